@@ -1,0 +1,817 @@
+// b2exec.cu — host runtime + C ABI (include/b2exec.h) of the B200 electron
+// executor.  One translation unit: the kernels live in b2_spans.cuh (K1/K2/K4)
+// and b2_worker.cuh (K3).
+//
+// Build (see covalent_ssh_plugin_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+//        -Xcompiler -fPIC -shared -o libb2exec.so b2exec.cu
+//
+// Per device the runtime owns: one compute stream (every kernel of the library
+// runs on it, in call order), the device arena, two pinned staging buffers,
+// the task table / successor list / status array, the MPMC queue cells and the
+// callback table.  Host-side tables that a kernel reads are staged through
+// small event-guarded pinned rings so that calls never block on the GPU unless
+// the ring wraps.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2_spans.cuh"
+#include "b2_worker.cuh"
+
+namespace {
+
+using namespace b2;
+
+thread_local std::string g_err = "";
+
+int fail(int code, const char *fmt, ...) {
+  char buf[768];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(B2_E_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,    \
+                  __LINE__);                                                                  \
+  } while (0)
+
+constexpr int kMaxDevices = 16;
+constexpr int kRing = 4;          // staging ring depth
+constexpr int kTickets = 4096;    // completion events kept alive
+constexpr int kMaxUserEvents = 256;
+
+// A pinned host buffer with a device mirror, guarded by an event so it is not
+// rewritten while an earlier async copy may still be reading it.
+struct Staging {
+  uint8_t *h = nullptr;
+  uint8_t *d = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool in_flight = false;
+};
+
+struct Device {
+  std::mutex mu;
+  bool up = false;
+  int dev = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+
+  uint8_t *h_in = nullptr, *h_out = nullptr;
+  uint64_t h_in_bytes = 0, h_out_bytes = 0;
+
+  // arena 0 is local; 1.. are mapped peers
+  uint8_t *arena[B2_MAX_ARENAS] = {};
+  uint64_t arena_bytes[B2_MAX_ARENAS] = {};
+  int arena_owner_dev[B2_MAX_ARENAS] = {};
+  bool arena_ipc[B2_MAX_ARENAS] = {};
+  int n_arenas = 0;
+
+  // queue + callback table
+  unsigned long long *d_cells = nullptr;
+  uint32_t *d_head = nullptr, *d_tail = nullptr, *d_cursor = nullptr;
+  unsigned long long *d_retired = nullptr;
+  uint32_t qcap = 0;
+  unsigned long long retired_total = 0;
+  FnEntry *d_fn = nullptr;
+  uint32_t *d_status = nullptr;
+
+  // pending batch: [qcap tasks][succ_cap successor indices]
+  Staging task_ring[kRing];
+  int task_slot = 0;
+  uint32_t pend_tasks = 0, pend_succ = 0, succ_cap = 0;
+
+  Staging span_ring[kRing];
+  int span_slot = 0;
+
+  int worker_ctas_per_sm = 0;
+  int mover_ctas_per_sm = 0;
+  int mover_unroll = 8;
+
+  cudaEvent_t tickets[kTickets] = {};
+  uint64_t next_ticket = 1;
+  cudaEvent_t user_ev[kMaxUserEvents] = {};
+  uint32_t n_user_ev = 0;
+
+  b2_stats stats = {};
+};
+
+Device g_dev[kMaxDevices];
+
+Device *get(int dev) {
+  if (dev < 0 || dev >= kMaxDevices) return nullptr;
+  return &g_dev[dev];
+}
+
+#define DEV_OR_FAIL(D, dev)                                              \
+  Device *D = get(dev);                                                  \
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);  \
+  std::lock_guard<std::mutex> lock_(D->mu);                              \
+  if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev); \
+  CU(cudaSetDevice(dev))
+
+int staging_reserve(Staging &s, size_t bytes) {
+  if (s.in_flight) {
+    CU(cudaEventSynchronize(s.ev));
+    s.in_flight = false;
+  }
+  if (!s.ev) CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  if (bytes > s.cap) {
+    size_t ncap = std::max<size_t>(bytes, s.cap * 2);
+    ncap = (ncap + 4095) & ~size_t(4095);
+    if (s.h) cudaFreeHost(s.h);
+    if (s.d) cudaFree(s.d);
+    s.h = nullptr;
+    s.d = nullptr;
+    s.cap = 0;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&s.h), ncap, cudaHostAllocDefault));
+    CU(cudaMalloc(reinterpret_cast<void **>(&s.d), ncap));
+    s.cap = ncap;
+  }
+  return B2_OK;
+}
+
+void staging_free(Staging &s) {
+  if (s.h) cudaFreeHost(s.h);
+  if (s.d) cudaFree(s.d);
+  if (s.ev) cudaEventDestroy(s.ev);
+  s = Staging();
+}
+
+template <int UNROLL>
+void launch_mover(Device *D, const SpanDev *spans, const uint32_t *base, uint32_t n, uint32_t chunks,
+                  uint32_t cps, int grid) {
+  span_move_kernel<UNROLL><<<grid, kMoveThreads, 0, D->stream>>>(spans, base, n, chunks, cps);
+}
+
+// Builds the device span table for n spans (src in arena src_id, dst in arena
+// dst_id), uploads it and launches the mover.  Caller holds the device lock.
+int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_id,
+                      uint32_t dst_id) {
+  if (n == 0) return B2_OK;
+  if (!spans) return fail(B2_E_ARG, "spans is NULL");
+  if (src_id >= (uint32_t)D->n_arenas || dst_id >= (uint32_t)D->n_arenas)
+    return fail(B2_E_ARG, "arena id out of range (src %u, dst %u, have %d)", src_id, dst_id,
+                D->n_arenas);
+  const size_t table_bytes = (size_t)n * sizeof(SpanDev);
+  const size_t base_off = (table_bytes + 255) & ~size_t(255);
+  const size_t total = base_off + ((size_t)n + 1) * sizeof(uint32_t);
+  Staging &s = D->span_ring[D->span_slot];
+  int rc = staging_reserve(s, total);
+  if (rc) return rc;
+  D->span_slot = (D->span_slot + 1) % kRing;
+
+  SpanDev *tab = reinterpret_cast<SpanDev *>(s.h);
+  uint32_t *base = reinterpret_cast<uint32_t *>(s.h + base_off);
+  uint64_t chunks = 0, moved = 0;
+  bool uniform = true;
+  const uint64_t b0 = spans[0].bytes;
+  for (uint32_t i = 0; i < n; ++i) {
+    const b2_span &sp = spans[i];
+    if (sp.src_off + sp.bytes > D->arena_bytes[src_id] || sp.src_off + sp.bytes < sp.src_off)
+      return fail(B2_E_ARG, "span %u: source [%llu, +%llu) outside arena %u (%llu bytes)", i,
+                  (unsigned long long)sp.src_off, (unsigned long long)sp.bytes, src_id,
+                  (unsigned long long)D->arena_bytes[src_id]);
+    if (sp.dst_off + sp.bytes > D->arena_bytes[dst_id] || sp.dst_off + sp.bytes < sp.dst_off)
+      return fail(B2_E_ARG, "span %u: destination [%llu, +%llu) outside arena %u (%llu bytes)", i,
+                  (unsigned long long)sp.dst_off, (unsigned long long)sp.bytes, dst_id,
+                  (unsigned long long)D->arena_bytes[dst_id]);
+    tab[i].src = D->arena[src_id] + sp.src_off;
+    tab[i].dst = D->arena[dst_id] + sp.dst_off;
+    tab[i].bytes = sp.bytes;
+    tab[i].chunk_base = (uint32_t)chunks;
+    tab[i].pad = 0;
+    base[i] = (uint32_t)chunks;
+    chunks += (sp.bytes + kChunkBytes - 1) / kChunkBytes;
+    moved += sp.bytes;
+    uniform = uniform && (sp.bytes == b0);
+    if (chunks > 0xFFFFFFF0ull) return fail(B2_E_NOMEM, "too many chunks in one span move");
+  }
+  base[n] = (uint32_t)chunks;
+  if (chunks == 0) return B2_OK;
+
+  CU(cudaMemcpyAsync(s.d, s.h, total, cudaMemcpyHostToDevice, D->stream));
+  CU(cudaEventRecord(s.ev, D->stream));
+  s.in_flight = true;
+
+  const uint32_t cps = uniform ? (uint32_t)((b0 + kChunkBytes - 1) / kChunkBytes) : 0u;
+  const int warps_per_cta = kMoveThreads / kWarp;
+  const uint64_t want = (chunks + warps_per_cta - 1) / warps_per_cta;
+  const int cap = D->sm_count * std::max(1, D->mover_ctas_per_sm);
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)cap);
+  const SpanDev *dtab = reinterpret_cast<const SpanDev *>(s.d);
+  const uint32_t *dbase = reinterpret_cast<const uint32_t *>(s.d + base_off);
+  switch (D->mover_unroll) {
+    case 4: launch_mover<4>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
+    case 16: launch_mover<16>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
+    default: launch_mover<8>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
+  }
+  CU(cudaGetLastError());
+  D->stats.launches_pack += 1;
+  D->stats.bytes_packed += moved;
+  return B2_OK;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+}  // namespace
+
+// =============================================================== C ABI =====
+extern "C" {
+
+const char *b2_last_error(void) { return g_err.c_str(); }
+int b2_abi_version(void) { return (int)B2_ABI_VERSION; }
+
+int b2_device_count(int *count) {
+  if (!count) return fail(B2_E_ARG, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(B2_E_CUDA, "cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return B2_OK;
+}
+
+int b2_is_initialized(int dev) {
+  Device *D = get(dev);
+  if (!D) return 0;
+  std::lock_guard<std::mutex> lock_(D->mu);
+  return D->up ? 1 : 0;
+}
+
+int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t staging_out_bytes,
+            uint32_t queue_cap) {
+  Device *D = get(dev);
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock_(D->mu);
+  if (D->up) return fail(B2_E_STATE, "device %d is already initialised", dev);
+  if (queue_cap < 2 || (queue_cap & (queue_cap - 1)))
+    return fail(B2_E_ARG, "queue_cap must be a power of two >= 2 (got %u)", queue_cap);
+  if (arena_bytes < 4096 || (arena_bytes & 255))
+    return fail(B2_E_ARG, "arena_bytes must be a multiple of 256 and >= 4096");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (dev >= ndev) return fail(B2_E_ARG, "no CUDA device %d (have %d)", dev, ndev);
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10)
+    return fail(B2_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                dev, prop.major, prop.minor);
+  D->dev = dev;
+  D->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->arena[0]), arena_bytes));
+  D->arena_bytes[0] = arena_bytes;
+  D->arena_owner_dev[0] = dev;
+  D->n_arenas = 1;
+  if (staging_in_bytes) {
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&D->h_in), staging_in_bytes, cudaHostAllocDefault));
+    D->h_in_bytes = staging_in_bytes;
+  }
+  if (staging_out_bytes) {
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&D->h_out), staging_out_bytes,
+                     cudaHostAllocDefault));
+    D->h_out_bytes = staging_out_bytes;
+  }
+
+  D->qcap = queue_cap;
+  D->succ_cap = queue_cap * 4u;
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_cells), (size_t)queue_cap * 8));
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_head), 256));
+  D->d_tail = D->d_head + 16;     // separate 64 B sectors
+  D->d_cursor = D->d_head + 32;
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_retired), 64));
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_fn), sizeof(FnEntry) * B2_MAX_FN));
+  CU(cudaMemsetAsync(D->d_fn, 0, sizeof(FnEntry) * B2_MAX_FN, D->stream));
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_status), (size_t)queue_cap * 4));
+  queue_init_kernel<<<(queue_cap + 255) / 256, 256, 0, D->stream>>>(D->d_cells, queue_cap,
+                                                                   D->d_head, D->d_tail,
+                                                                   D->d_retired);
+  CU(cudaGetLastError());
+  D->stats = b2_stats();
+  D->stats.launches_other = 1;
+  D->retired_total = 0;
+  D->pend_tasks = D->pend_succ = 0;
+  D->task_slot = D->span_slot = 0;
+  D->next_ticket = 1;
+  D->n_user_ev = 0;
+
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_kernel,
+                                                   kWorkerThreads, 0));
+  D->mover_unroll = env_int("B2_MOVER_UNROLL", 8);
+  if (D->mover_unroll != 4 && D->mover_unroll != 16) D->mover_unroll = 8;
+  switch (D->mover_unroll) {
+    case 4:
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->mover_ctas_per_sm, span_move_kernel<4>,
+                                                       kMoveThreads, 0));
+      break;
+    case 16:
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->mover_ctas_per_sm,
+                                                       span_move_kernel<16>, kMoveThreads, 0));
+      break;
+    default:
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->mover_ctas_per_sm, span_move_kernel<8>,
+                                                       kMoveThreads, 0));
+  }
+  const int wcap = env_int("B2_WORKER_CTAS_PER_SM", 0);
+  if (wcap > 0) D->worker_ctas_per_sm = std::min(D->worker_ctas_per_sm, wcap);
+  const int mcap = env_int("B2_MOVER_CTAS_PER_SM", 0);
+  if (mcap > 0) D->mover_ctas_per_sm = std::min(D->mover_ctas_per_sm, mcap);
+
+  // gate electron: fn_id 0 is a registered no-op (kind NONE) used to fan a
+  // dependency out to many successors.
+  CU(cudaStreamSynchronize(D->stream));
+  D->up = true;
+  return B2_OK;
+}
+
+int b2_shutdown(int dev) {
+  Device *D = get(dev);
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock_(D->mu);
+  if (!D->up) return fail(B2_E_STATE, "device %d is not initialised", dev);
+  cudaSetDevice(dev);
+  cudaStreamSynchronize(D->stream);
+  for (int i = 1; i < D->n_arenas; ++i)
+    if (D->arena_ipc[i] && D->arena[i]) cudaIpcCloseMemHandle(D->arena[i]);
+  for (auto &s : D->task_ring) staging_free(s);
+  for (auto &s : D->span_ring) staging_free(s);
+  for (auto &e : D->tickets)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (uint32_t i = 0; i < D->n_user_ev; ++i)
+    if (D->user_ev[i]) { cudaEventDestroy(D->user_ev[i]); D->user_ev[i] = nullptr; }
+  cudaFree(D->arena[0]);
+  if (D->h_in) cudaFreeHost(D->h_in);
+  if (D->h_out) cudaFreeHost(D->h_out);
+  cudaFree(D->d_cells);
+  cudaFree(D->d_head);
+  cudaFree(D->d_retired);
+  cudaFree(D->d_fn);
+  cudaFree(D->d_status);
+  cudaStreamDestroy(D->stream);
+  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
+    D->arena[i] = nullptr;
+    D->arena_bytes[i] = 0;
+    D->arena_ipc[i] = false;
+  }
+  D->h_in = D->h_out = nullptr;
+  D->h_in_bytes = D->h_out_bytes = 0;
+  D->n_arenas = 0;
+  D->up = false;
+  return B2_OK;
+}
+
+int b2_get_info(int dev, b2_device_info *out) {
+  if (!out) return fail(B2_E_ARG, "out is NULL");
+  DEV_OR_FAIL(D, dev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  memset(out, 0, sizeof *out);
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  out->sm_count = prop.multiProcessorCount;
+  out->l2_bytes_mb = prop.l2CacheSize >> 20;
+  out->total_mem = prop.totalGlobalMem;
+  out->arena_bytes = D->arena_bytes[0];
+  out->staging_in_bytes = D->h_in_bytes;
+  out->staging_out_bytes = D->h_out_bytes;
+  out->queue_cap = D->qcap;
+  out->abi_version = B2_ABI_VERSION;
+  strncpy(out->name, prop.name, sizeof(out->name) - 1);
+  return B2_OK;
+}
+
+int b2_get_stats(int dev, b2_stats *out) {
+  if (!out) return fail(B2_E_ARG, "out is NULL");
+  DEV_OR_FAIL(D, dev);
+  *out = D->stats;
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------ memory --
+int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes) {
+  if (!ptr || !bytes) return fail(B2_E_ARG, "ptr/bytes is NULL");
+  DEV_OR_FAIL(D, dev);
+  if (which == 0) {
+    *ptr = D->h_in;
+    *bytes = D->h_in_bytes;
+  } else if (which == 1) {
+    *ptr = D->h_out;
+    *bytes = D->h_out_bytes;
+  } else {
+    return fail(B2_E_ARG, "which must be 0 (ingress) or 1 (egress)");
+  }
+  return B2_OK;
+}
+
+int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (host_off + bytes > D->h_in_bytes || host_off + bytes < host_off)
+    return fail(B2_E_ARG, "h2d: host range [%llu, +%llu) outside ingress staging (%llu bytes)",
+                (unsigned long long)host_off, (unsigned long long)bytes,
+                (unsigned long long)D->h_in_bytes);
+  if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
+    return fail(B2_E_ARG, "h2d: device range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemcpyAsync(D->arena[0] + dev_off, D->h_in + host_off, bytes, cudaMemcpyHostToDevice,
+                     D->stream));
+  D->stats.bytes_h2d += bytes;
+  return B2_OK;
+}
+
+int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (host_off + bytes > D->h_out_bytes || host_off + bytes < host_off)
+    return fail(B2_E_ARG, "d2h: host range [%llu, +%llu) outside egress staging (%llu bytes)",
+                (unsigned long long)host_off, (unsigned long long)bytes,
+                (unsigned long long)D->h_out_bytes);
+  if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
+    return fail(B2_E_ARG, "d2h: device range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemcpyAsync(D->h_out + host_off, D->arena[0] + dev_off, bytes, cudaMemcpyDeviceToHost,
+                     D->stream));
+  D->stats.bytes_d2h += bytes;
+  return B2_OK;
+}
+
+int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (!src && bytes) return fail(B2_E_ARG, "src is NULL");
+  if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
+    return fail(B2_E_ARG, "write: device range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemcpyAsync(D->arena[0] + dev_off, src, bytes, cudaMemcpyHostToDevice, D->stream));
+  CU(cudaStreamSynchronize(D->stream));
+  return B2_OK;
+}
+
+int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (!dst && bytes) return fail(B2_E_ARG, "dst is NULL");
+  if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
+    return fail(B2_E_ARG, "read: device range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemcpyAsync(dst, D->arena[0] + dev_off, bytes, cudaMemcpyDeviceToHost, D->stream));
+  CU(cudaStreamSynchronize(D->stream));
+  return B2_OK;
+}
+
+int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
+    return fail(B2_E_ARG, "fill: device range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemsetAsync(D->arena[0] + dev_off, byte_value, bytes, D->stream));
+  return B2_OK;
+}
+
+// ----------------------------------------------------------- pack / unpack --
+int b2_move_spans(int dev, const b2_span *spans, uint32_t n) {
+  DEV_OR_FAIL(D, dev);
+  return move_spans_locked(D, spans, n, 0, 0);
+}
+
+static int pack_like(int dev, bool gather, const uint64_t *scattered, const uint64_t *sizes,
+                     uint32_t n, uint64_t run_off, uint32_t align, uint64_t *out_offs,
+                     uint64_t *out_total) {
+  if (n && (!scattered || !sizes)) return fail(B2_E_ARG, "offsets/sizes is NULL");
+  if (align == 0 || (align & (align - 1))) return fail(B2_E_ARG, "align must be a power of two");
+  DEV_OR_FAIL(D, dev);
+  std::vector<b2_span> spans(n);
+  uint64_t cur = run_off;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (gather) {
+      spans[i].src_off = scattered[i];
+      spans[i].dst_off = cur;
+    } else {
+      spans[i].src_off = cur;
+      spans[i].dst_off = scattered[i];
+    }
+    spans[i].bytes = sizes[i];
+    if (out_offs) out_offs[i] = cur;
+    cur += (sizes[i] + align - 1) & ~(uint64_t)(align - 1);
+  }
+  if (out_total) *out_total = cur - run_off;
+  return move_spans_locked(D, spans.data(), n, 0, 0);
+}
+
+int b2_pack(int dev, const uint64_t *src_offs, const uint64_t *sizes, uint32_t n, uint64_t dst_off,
+            uint32_t align, uint64_t *out_offs, uint64_t *out_total) {
+  return pack_like(dev, true, src_offs, sizes, n, dst_off, align, out_offs, out_total);
+}
+
+int b2_unpack(int dev, uint64_t src_off, const uint64_t *dst_offs, const uint64_t *sizes, uint32_t n,
+              uint32_t align, uint64_t *out_offs, uint64_t *out_total) {
+  return pack_like(dev, false, dst_offs, sizes, n, src_off, align, out_offs, out_total);
+}
+
+// -------------------------------------------------- callback table + queue --
+int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta, int64_t ialpha,
+                int64_t ibeta) {
+  DEV_OR_FAIL(D, dev);
+  if (fn_id >= B2_MAX_FN) return fail(B2_E_ARG, "fn_id %u >= B2_MAX_FN", fn_id);
+  if (kind < 0 || kind >= B2_K__COUNT) return fail(B2_E_ARG, "unknown callback kind %d", kind);
+  if (fn_id == 0 && kind != B2_K_NONE)
+    return fail(B2_E_ARG, "fn_id 0 is reserved for the gate electron");
+  FnEntry e;
+  memset(&e, 0, sizeof e);
+  e.kind = (uint32_t)kind;
+  e.alpha = (float)alpha;
+  e.beta = (float)beta;
+  e.ialpha = ialpha;
+  e.ibeta = ibeta;
+  // 32-byte entry: passing it by value through a synchronous copy keeps the
+  // host copy alive for the duration.
+  CU(cudaMemcpyAsync(D->d_fn + fn_id, &e, sizeof e, cudaMemcpyHostToDevice, D->stream));
+  CU(cudaStreamSynchronize(D->stream));
+  return B2_OK;
+}
+
+int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
+               uint32_t *first_index) {
+  DEV_OR_FAIL(D, dev);
+  if (n && !tasks) return fail(B2_E_ARG, "tasks is NULL");
+  if (n_succ && !succ) return fail(B2_E_ARG, "succ is NULL but n_succ = %u", n_succ);
+  if ((uint64_t)D->pend_tasks + n > D->qcap)
+    return fail(B2_E_NOMEM, "batch of %u + %u electrons exceeds queue capacity %u", D->pend_tasks,
+                n, D->qcap);
+  if ((uint64_t)D->pend_succ + n_succ > D->succ_cap)
+    return fail(B2_E_NOMEM, "successor list of %u + %u exceeds capacity %u", D->pend_succ, n_succ,
+                D->succ_cap);
+  Staging &s = D->task_ring[D->task_slot];
+  const size_t succ_off = (size_t)D->qcap * sizeof(b2_task);
+  if (D->pend_tasks == 0 && D->pend_succ == 0) {
+    int rc = staging_reserve(s, succ_off + (size_t)D->succ_cap * 4);
+    if (rc) return rc;
+  }
+  if (first_index) *first_index = D->pend_tasks;
+  b2_task *ht = reinterpret_cast<b2_task *>(s.h) + D->pend_tasks;
+  memcpy(ht, tasks, (size_t)n * sizeof(b2_task));
+  // successor ranges are given relative to this call's succ array
+  for (uint32_t i = 0; i < n; ++i) {
+    if (ht[i].succ_count) {
+      if ((uint64_t)ht[i].succ_begin + ht[i].succ_count > n_succ)
+        return fail(B2_E_ARG, "task %u: successor range [%u, +%u) outside succ[%u]", i,
+                    ht[i].succ_begin, ht[i].succ_count, n_succ);
+      ht[i].succ_begin += D->pend_succ;
+    }
+    if (ht[i].deps) {
+      if (ht[i].deps >= kDepBias) return fail(B2_E_ARG, "task %u: deps too large", i);
+      ht[i].deps += kDepBias;  // see kDepBias in b2_device.cuh
+    }
+  }
+  if (n_succ)
+    memcpy(reinterpret_cast<uint32_t *>(s.h + succ_off) + D->pend_succ, succ, (size_t)n_succ * 4);
+  D->pend_tasks += n;
+  D->pend_succ += n_succ;
+  return B2_OK;
+}
+
+static int record_ticket(Device *D, uint64_t *ticket) {
+  const uint64_t t = D->next_ticket++;
+  cudaEvent_t &ev = D->tickets[t % kTickets];
+  if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, D->stream));
+  if (ticket) *ticket = t;
+  return B2_OK;
+}
+
+int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
+  DEV_OR_FAIL(D, dev);
+  const uint32_t n = D->pend_tasks;
+  if (n == 0) return record_ticket(D, ticket);
+  if (status_host_off != UINT64_MAX &&
+      (status_host_off + (uint64_t)n * 4 > D->h_out_bytes || (status_host_off & 3)))
+    return fail(B2_E_ARG, "status_host_off %llu (+%u words) outside egress staging",
+                (unsigned long long)status_host_off, n);
+  Staging &s = D->task_ring[D->task_slot];
+  const size_t succ_off = (size_t)D->qcap * sizeof(b2_task);
+  CU(cudaMemcpyAsync(s.d, s.h, (size_t)n * sizeof(b2_task), cudaMemcpyHostToDevice, D->stream));
+  if (D->pend_succ)
+    CU(cudaMemcpyAsync(s.d + succ_off, s.h + succ_off, (size_t)D->pend_succ * 4,
+                       cudaMemcpyHostToDevice, D->stream));
+  CU(cudaEventRecord(s.ev, D->stream));
+  s.in_flight = true;
+  CU(cudaMemsetAsync(D->d_cursor, 0, 4, D->stream));
+
+  WorkerArgs a;
+  memset(&a, 0, sizeof a);
+  a.tasks = reinterpret_cast<b2_task *>(s.d);
+  a.succ = reinterpret_cast<const uint32_t *>(s.d + succ_off);
+  a.status = D->d_status;
+  a.fn_table = D->d_fn;
+  a.q.cells = D->d_cells;
+  a.q.head = D->d_head;
+  a.q.tail = D->d_tail;
+  a.q.retired = D->d_retired;
+  a.q.mask = D->qcap - 1;
+  a.cursor = D->d_cursor;
+  a.n_tasks = n;
+  D->retired_total += n;
+  a.retire_target = D->retired_total;
+  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
+    a.arena[i] = D->arena[i];
+    a.arena_bytes[i] = D->arena_bytes[i];
+  }
+  const int cap = D->sm_count * std::max(1, D->worker_ctas_per_sm);
+  const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
+  worker_kernel<<<grid, kWorkerThreads, 0, D->stream>>>(a);
+  CU(cudaGetLastError());
+  D->stats.launches_worker += 1;
+  D->stats.electrons += n;
+  if (status_host_off != UINT64_MAX) {
+    CU(cudaMemcpyAsync(D->h_out + status_host_off, D->d_status, (size_t)n * 4,
+                       cudaMemcpyDeviceToHost, D->stream));
+    D->stats.bytes_d2h += (uint64_t)n * 4;
+  }
+  D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
+  D->task_slot = (D->task_slot + 1) % kRing;
+  D->pend_tasks = D->pend_succ = 0;
+  return record_ticket(D, ticket);
+}
+
+int b2_mark(int dev, uint64_t *ticket) {
+  DEV_OR_FAIL(D, dev);
+  return record_ticket(D, ticket);
+}
+
+int b2_poll(int dev, uint64_t ticket) {
+  DEV_OR_FAIL(D, dev);
+  if (ticket == 0 || ticket >= D->next_ticket) return fail(B2_E_ARG, "unknown ticket %llu",
+                                                           (unsigned long long)ticket);
+  if (D->next_ticket - ticket >= (uint64_t)kTickets) return B2_OK;  // event slot recycled: long done
+  cudaError_t e = cudaEventQuery(D->tickets[ticket % kTickets]);
+  if (e == cudaSuccess) return B2_OK;
+  if (e == cudaErrorNotReady) return B2_E_NOTREADY;
+  return fail(B2_E_CUDA, "cudaEventQuery -> %s", cudaGetErrorString(e));
+}
+
+int b2_wait(int dev, uint64_t ticket) {
+  cudaEvent_t ev = nullptr;
+  {
+    DEV_OR_FAIL(D, dev);
+    if (ticket == 0 || ticket >= D->next_ticket)
+      return fail(B2_E_ARG, "unknown ticket %llu", (unsigned long long)ticket);
+    if (D->next_ticket - ticket >= (uint64_t)kTickets) return B2_OK;
+    ev = D->tickets[ticket % kTickets];
+  }
+  // Block outside the device lock so other threads can keep submitting.
+  CU(cudaEventSynchronize(ev));
+  return B2_OK;
+}
+
+int b2_sync(int dev) {
+  cudaStream_t st;
+  {
+    DEV_OR_FAIL(D, dev);
+    st = D->stream;
+  }
+  CU(cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
+// ------------------------------------------------------------ peer routing --
+int b2_peer_enable(int dev, int peer_dev, uint32_t *arena_id) {
+  if (dev == peer_dev) return fail(B2_E_ARG, "peer_dev equals dev");
+  Device *P = get(peer_dev);
+  if (!P) return fail(B2_E_ARG, "peer ordinal %d out of range", peer_dev);
+  uint8_t *pbase;
+  uint64_t pbytes;
+  {
+    std::lock_guard<std::mutex> lk(P->mu);
+    if (!P->up) return fail(B2_E_STATE, "peer device %d is not initialised", peer_dev);
+    pbase = P->arena[0];
+    pbytes = P->arena_bytes[0];
+  }
+  DEV_OR_FAIL(D, dev);
+  for (int i = 1; i < D->n_arenas; ++i)
+    if (!D->arena_ipc[i] && D->arena_owner_dev[i] == peer_dev) {
+      if (arena_id) *arena_id = (uint32_t)i;
+      return B2_OK;
+    }
+  if (D->n_arenas >= B2_MAX_ARENAS) return fail(B2_E_NOMEM, "arena table full");
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, dev, peer_dev));
+  if (!can) return fail(B2_E_UNSUPPORTED, "device %d cannot access peer %d", dev, peer_dev);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+  } else if (e != cudaSuccess) {
+    return fail(B2_E_CUDA, "cudaDeviceEnablePeerAccess(%d) -> %s", peer_dev, cudaGetErrorString(e));
+  }
+  const int id = D->n_arenas++;
+  D->arena[id] = pbase;
+  D->arena_bytes[id] = pbytes;
+  D->arena_owner_dev[id] = peer_dev;
+  D->arena_ipc[id] = false;
+  if (arena_id) *arena_id = (uint32_t)id;
+  return B2_OK;
+}
+
+int b2_ipc_export(int dev, void *handle64) {
+  if (!handle64) return fail(B2_E_ARG, "handle64 is NULL");
+  DEV_OR_FAIL(D, dev);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, D->arena[0]));
+  memcpy(handle64, &h, 64);
+  return B2_OK;
+}
+
+int b2_ipc_open(int dev, const void *handle64, uint64_t peer_arena_bytes, uint32_t *arena_id) {
+  if (!handle64) return fail(B2_E_ARG, "handle64 is NULL");
+  DEV_OR_FAIL(D, dev);
+  if (D->n_arenas >= B2_MAX_ARENAS) return fail(B2_E_NOMEM, "arena table full");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  const int id = D->n_arenas++;
+  D->arena[id] = static_cast<uint8_t *>(p);
+  D->arena_bytes[id] = peer_arena_bytes;
+  D->arena_owner_dev[id] = -1;
+  D->arena_ipc[id] = true;
+  if (arena_id) *arena_id = (uint32_t)id;
+  return B2_OK;
+}
+
+int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_off,
+                 uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (dst_arena_id >= (uint32_t)D->n_arenas) return fail(B2_E_ARG, "unknown arena id %u", dst_arena_id);
+  if (src_off + bytes > D->arena_bytes[0] || dst_off + bytes > D->arena_bytes[dst_arena_id])
+    return fail(B2_E_ARG, "peer_copy: range outside arena");
+  if (!bytes) return B2_OK;
+  CU(cudaMemcpyAsync(D->arena[dst_arena_id] + dst_off, D->arena[0] + src_off, bytes,
+                     cudaMemcpyDefault, D->stream));
+  return B2_OK;
+}
+
+int b2_peer_pack(int dev, uint32_t dst_arena_id, const b2_span *spans, uint32_t n) {
+  DEV_OR_FAIL(D, dev);
+  return move_spans_locked(D, spans, n, 0, dst_arena_id);
+}
+
+// ------------------------------------------------------------- measurement --
+int b2_event_create(int dev, uint32_t *event_id) {
+  if (!event_id) return fail(B2_E_ARG, "event_id is NULL");
+  DEV_OR_FAIL(D, dev);
+  if (D->n_user_ev >= (uint32_t)kMaxUserEvents) return fail(B2_E_NOMEM, "too many events");
+  CU(cudaEventCreate(&D->user_ev[D->n_user_ev]));
+  *event_id = D->n_user_ev++;
+  return B2_OK;
+}
+
+int b2_event_record(int dev, uint32_t event_id) {
+  DEV_OR_FAIL(D, dev);
+  if (event_id >= D->n_user_ev) return fail(B2_E_ARG, "unknown event %u", event_id);
+  CU(cudaEventRecord(D->user_ev[event_id], D->stream));
+  return B2_OK;
+}
+
+int b2_event_elapsed_ms(int dev, uint32_t start_id, uint32_t stop_id, float *ms) {
+  if (!ms) return fail(B2_E_ARG, "ms is NULL");
+  cudaEvent_t a, b;
+  {
+    DEV_OR_FAIL(D, dev);
+    if (start_id >= D->n_user_ev || stop_id >= D->n_user_ev)
+      return fail(B2_E_ARG, "unknown event id");
+    a = D->user_ev[start_id];
+    b = D->user_ev[stop_id];
+  }
+  CU(cudaEventSynchronize(b));
+  CU(cudaEventElapsedTime(ms, a, b));
+  return B2_OK;
+}
+
+int b2_flush_l2(int dev, uint64_t scratch_off, uint64_t bytes) {
+  DEV_OR_FAIL(D, dev);
+  if (scratch_off + bytes > D->arena_bytes[0]) return fail(B2_E_ARG, "flush range outside arena");
+  static int v = 0;
+  CU(cudaMemsetAsync(D->arena[0] + scratch_off, (++v) & 0xff, bytes, D->stream));
+  return B2_OK;
+}
+
+}  // extern "C"

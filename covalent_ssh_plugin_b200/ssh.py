@@ -1,0 +1,456 @@
+"""SSHExecutor for B200 "hosts": the reference's executor-plugin surface, with the
+per-electron SSH pipeline replaced by the CUDA engine.
+
+Drop-in for /root/reference/covalent_ssh_plugin/ssh.py: same module attributes
+(``EXECUTOR_PLUGIN_NAME`` ssh.py:34, ``_EXECUTOR_PLUGIN_DEFAULTS`` ssh.py:39-50),
+same constructor signature and resolution order (ssh.py:75-124), same public
+and patchable method names, same error behaviour.  What changes is what a
+"remote host" is: ``hostname`` names one of the box's GPUs (``"cuda:3"``,
+``"gpu:3"``, ``"b200:3"``, ``"localhost"`` = this process's default GPU), the
+"connection" is that GPU's process-wide engine (engine.py), the "function
+file" is a 64-byte task record plus raw operand bytes in pinned memory, and
+"running the script" is the persistent worker kernel calling the electron's
+registered device callback.
+
+Reference step (ssh.py)                      -> here
+  _validate_credentials 317-335              -> unchanged contract (key file must exist)
+  _client_connect / _attempt_client_connect  -> open (or reuse) the GPU engine, same retry loop
+  conda / python --version / mkdir 508-532   -> one capability probe when the engine opens
+  _write_function_files 126-179              -> encode the call, derive the same five names
+  _upload_task 337-361                       -> stage operands in pinned ingress memory
+  submit_task 363-386                        -> join the batch, await its completion
+  _poll_task / get_status 388-432            -> completion flag of the batch ticket
+  query_result 434-458                       -> decode the result out of pinned egress memory
+  cleanup 284-315                            -> release the staging segment reference
+  _on_ssh_fail 181-208                       -> unchanged
+"""
+
+from __future__ import annotations
+
+import asyncio
+import logging
+import os
+import socket
+from pathlib import Path
+from typing import Any, Callable, Coroutine, Dict, Optional, Tuple, Union
+
+from . import _b2lib
+from .electrons import NotDeviceEligible, encode
+from .engine import DeviceEngine, Staged, get_engine
+
+try:  # the real Covalent SDK, when installed
+    from covalent._shared_files import logger as _cov_logger
+    from covalent._shared_files.config import get_config
+    from covalent.executor.executor_plugins.remote_executor import RemoteExecutor
+
+    app_log = _cov_logger.app_log
+    log_stack_info = _cov_logger.log_stack_info
+    HAVE_COVALENT = True
+except Exception:  # stand-ins with the same call surface
+    from ._covalent_compat import RemoteExecutor, app_log, get_config, log_stack_info
+
+    HAVE_COVALENT = False
+
+EXECUTOR_PLUGIN_NAME = "SSHExecutor"
+
+
+def _default_cache_dir() -> str:
+    return str(Path(get_config("dispatcher.cache_dir")).expanduser().resolve())
+
+
+_EXECUTOR_PLUGIN_DEFAULTS = {
+    "username": "",
+    "hostname": "",
+    "ssh_key_file": os.path.join(os.environ["HOME"], ".ssh/id_rsa"),
+    "cache_dir": _default_cache_dir(),
+    "python_path": "python",
+    "conda_env": "",
+    "remote_cache": ".cache/covalent",
+    "run_local_on_ssh_fail": False,
+    "remote_workdir": "covalent-workdir",
+    "create_unique_workdir": False,
+}
+
+_LOCAL_NAMES = ("", "localhost", "127.0.0.1", "::1")
+_GPU_PREFIXES = ("cuda:", "gpu:", "b200:", "cuda", "gpu", "b200")
+
+
+def resolve_device(hostname: str) -> int:
+    """CUDA ordinal named by ``hostname``.  Names that are not GPU names resolve
+    the way an unknown DNS name does in the reference: ``socket.gaierror``."""
+    h = (hostname or "").strip().lower()
+    if h in _LOCAL_NAMES:
+        return int(os.environ.get("LOCAL_RANK", os.environ.get("B2_DEFAULT_DEVICE", "0")))
+    for p in _GPU_PREFIXES:
+        if h.startswith(p) and h[len(p):].isdigit():
+            return int(h[len(p):])
+    raise socket.gaierror(f"'{hostname}' does not name a GPU of this box (use 'cuda:N')")
+
+
+class DeviceConnection:
+    """What ``_client_connect`` hands out: a handle on the GPU's engine.  Closing
+    it does not tear the engine down — not re-handshaking per electron is the
+    point — so ``close``/``wait_closed`` only mirror ssh.py:585-587."""
+
+    __slots__ = ("engine", "hostname")
+
+    def __init__(self, engine: DeviceEngine, hostname: str):
+        self.engine = engine
+        self.hostname = hostname
+
+    def close(self) -> None:
+        return None
+
+    async def wait_closed(self) -> bool:
+        return True
+
+
+class CompletedElectron:
+    """Stand-in for asyncssh.SSHCompletedProcess (ssh.py:363-386)."""
+
+    __slots__ = ("exit_status", "returncode", "stdout", "stderr")
+
+    def __init__(self, exit_status: int, stderr: str = "", stdout: str = ""):
+        self.exit_status = exit_status
+        self.returncode = exit_status
+        self.stdout = stdout
+        self.stderr = stderr
+
+
+class _InFlight:
+    """Book-keeping for one electron between the helper calls of ``run``; keyed
+    by the same artefact names the reference uses as file names."""
+
+    __slots__ = ("encoded", "staged", "reason")
+
+    def __init__(self, encoded=None, reason: str = ""):
+        self.encoded = encoded
+        self.staged: Optional[Staged] = None
+        self.reason = reason
+
+
+# name (any of the five artefact names) -> _InFlight; process-wide like a cache dir
+_inflight: Dict[str, _InFlight] = {}
+
+
+class SSHExecutor(RemoteExecutor):
+    """Runs electrons on a B200 instead of on an SSH host.
+
+    Args (identical to the reference, ssh.py:56-73):
+        username: accepted for compatibility; GPUs have no users.
+        hostname: which GPU: ``"cuda:N"`` / ``"gpu:N"`` / ``"b200:N"``, or
+            ``"localhost"`` for this process's default device.
+        ssh_key_file: must name an existing file, as in the reference.
+        cache_dir: local directory name used to derive artefact names.
+        python_path, conda_env: kept as attributes; no interpreter is spawned.
+        remote_cache: name of the "remote" artefact directory.
+        run_local_on_ssh_fail: run the electron in this process when the device
+            path cannot take it, instead of raising ``RuntimeError``.
+        remote_workdir, create_unique_workdir: workdir naming, as the reference.
+        poll_freq: seconds between completion polls after a failed poll.
+        do_cleanup: release per-electron staging state after the result is read.
+        retry_connect, max_connection_attempts, retry_wait_time: retry policy for
+            opening the device engine.
+    """
+
+    def __init__(
+        self,
+        username: str,
+        hostname: str,
+        ssh_key_file: str = None,
+        cache_dir: str = None,
+        python_path: str = "",
+        conda_env: str = None,
+        remote_cache: str = "",
+        run_local_on_ssh_fail: bool = False,
+        remote_workdir: str = "",
+        create_unique_workdir: Optional[bool] = None,
+        poll_freq: int = 15,
+        do_cleanup: bool = True,
+        retry_connect: bool = True,
+        max_connection_attempts: int = 5,
+        retry_wait_time: int = 5,
+    ) -> None:
+        cfg = lambda key: get_config(f"executors.ssh.{key}")  # noqa: E731
+
+        remote_cache = remote_cache or cfg("remote_cache") or ".cache/covalent"
+        super().__init__(poll_freq=poll_freq, remote_cache=remote_cache)
+
+        # explicit argument, else user config, else built-in default
+        self.username = username or cfg("username")
+        self.hostname = hostname or cfg("hostname")
+        self.python_path = python_path or cfg("python_path") or "python"
+        self.conda_env = conda_env or cfg("conda_env")
+        self.cache_dir = str(Path(cache_dir or get_config("dispatcher.cache_dir")).expanduser().resolve())
+        self.run_local_on_ssh_fail = run_local_on_ssh_fail
+        self.remote_workdir = remote_workdir or cfg("remote_workdir")
+        self.create_unique_workdir = (
+            cfg("create_unique_workdir") if create_unique_workdir is None else create_unique_workdir
+        )
+        self.do_cleanup = do_cleanup
+        self.retry_connect = retry_connect
+        self.max_connection_attempts = max_connection_attempts
+        self.retry_wait_time = retry_wait_time
+        self.ssh_key_file = str(Path(ssh_key_file or cfg("ssh_key_file")).expanduser().resolve())
+
+    # ---------------------------------------------------------------- naming --
+    def _write_function_files(
+        self,
+        operation_id: str,
+        fn: Callable,
+        args: list,
+        kwargs: dict,
+        current_remote_workdir: str = ".",
+    ) -> Tuple[str, str, str, str, str]:
+        """Encode the call and derive the five artefact names (ssh.py:126-179).
+
+        Nothing is written to disk: the "function file" is the encoded task
+        record, registered under the names the reference would have used so the
+        later steps find it.  An electron that cannot run on the device is
+        recorded with the reason; ``submit_task`` reports it as a failed run.
+        """
+        function_file = os.path.join(self.cache_dir, f"function_{operation_id}.pkl")
+        script_file = os.path.join(self.cache_dir, f"exec_{operation_id}.py")
+        remote_function_file = os.path.join(self.remote_cache, f"function_{operation_id}.pkl")
+        remote_script_file = os.path.join(self.remote_cache, f"exec_{operation_id}.py")
+        remote_result_file = os.path.join(self.remote_cache, f"result_{operation_id}.pkl")
+
+        try:
+            entry = _InFlight(encoded=encode(fn, args, kwargs))
+        except NotDeviceEligible as why:
+            entry = _InFlight(reason=str(why))
+        _inflight[function_file] = entry
+        _inflight[remote_script_file] = entry
+        _inflight[remote_result_file] = entry
+        return (function_file, script_file, remote_function_file, remote_script_file, remote_result_file)
+
+    # --------------------------------------------------------------- failure --
+    def _on_ssh_fail(
+        self,
+        fn: Callable,
+        args: list,
+        kwargs: dict,
+        message: str,
+    ) -> Union[Any, None]:
+        """Decide what a failed device run means (ssh.py:181-208): run the
+        electron in this process if the user opted in, else ``RuntimeError``."""
+        if not self.run_local_on_ssh_fail:
+            app_log.error(message)
+            raise RuntimeError(message)
+        app_log.warning(message)
+        return fn(*args, **kwargs)
+
+    # ------------------------------------------------------------ connection --
+    async def _client_connect(self) -> Tuple[bool, Optional[DeviceConnection]]:
+        """Open (or reuse) the engine of the GPU named by ``hostname``
+        (ssh.py:210-235).  Returns ``(False, None)`` when it cannot be reached."""
+        if not os.path.exists(self.ssh_key_file):
+            message = f"SSH key file {self.ssh_key_file} does not exist."
+            app_log.error(message)
+            raise RuntimeError(message)
+        conn = None
+        try:
+            conn = await self._attempt_client_connect()
+        except (socket.gaierror, ValueError, TimeoutError) as err:
+            app_log.error(err)
+        return conn is not None, conn
+
+    async def _attempt_client_connect(self) -> Optional[DeviceConnection]:
+        """Retry loop around engine creation (ssh.py:237-282).  Errors that mean
+        "device busy / not there yet" are retried ``max_connection_attempts``
+        times, ``retry_wait_time`` seconds apart; with ``retry_connect=False``
+        the first one propagates.  A missing CUDA library is never retried or
+        swallowed: it raises ``LibraryMissing``."""
+        ordinal = resolve_device(self.hostname)
+        address = f"{self.username}@{self.hostname}"
+        for attempt in range(1, self.max_connection_attempts + 1):
+            try:
+                return await _open_engine(ordinal, self.hostname)
+            except (ConnectionRefusedError, OSError) as err:
+                if not self.retry_connect:
+                    app_log.error(f"{err} ({address} | retry disabled).")
+                    raise
+                app_log.warning(f"{err} ({address} | retry {attempt}/{self.max_connection_attempts})")
+                await asyncio.sleep(self.retry_wait_time)
+        return None
+
+    async def _validate_credentials(self) -> bool:
+        """The key file must exist (ssh.py:317-335)."""
+        if not Path(self.ssh_key_file).is_file():
+            raise RuntimeError(f"SSH key file {self.ssh_key_file} does not exist.")
+        return True
+
+    # ------------------------------------------------------------ the steps ---
+    async def _upload_task(
+        self,
+        conn: DeviceConnection,
+        function_file: str,
+        remote_function_file: str,
+        script_file: str,
+        remote_script_file: str,
+    ) -> None:
+        """Stage the electron's operands into pinned ingress memory and append
+        its task record to the open batch (replaces the two SCP uploads,
+        ssh.py:337-361).  The H2D copy itself happens once per batch."""
+        entry = _inflight.get(function_file)
+        if entry is None or entry.encoded is None:
+            return
+        engine = conn.engine
+        if not engine.fits(entry.encoded):
+            entry.reason = "payload larger than one staging segment"
+            entry.encoded = None
+            return
+        entry.staged = await engine.stage(entry.encoded)
+
+    async def submit_task(self, conn: DeviceConnection, remote_script_file: str) -> CompletedElectron:
+        """Wait for the batch holding this electron to retire on the device
+        (replaces ``conn.run("python exec_<id>.py")``, ssh.py:363-386)."""
+        entry = _inflight.get(remote_script_file)
+        if entry is None:
+            return CompletedElectron(127, f"{remote_script_file}: no such electron")
+        if entry.staged is None:
+            return CompletedElectron(126, entry.reason or "electron was not uploaded")
+        staged = entry.staged
+        batch = staged.batch
+        if not batch.done:
+            await batch.future
+        elif batch.error is not None:
+            raise batch.error
+        status = conn.engine.status_of(staged)
+        if status == _b2lib.TS_OK:
+            return CompletedElectron(0)
+        what = {_b2lib.TS_OVERFLOW: "integer result does not fit int64",
+                _b2lib.TS_BAD_FN: "no device callback registered for this electron",
+                _b2lib.TS_BAD_ARG: "operand rejected by the device callback"}.get(status, "device error")
+        return CompletedElectron(int(status) or 1, f"{staged.spec.name}: {what} (status {status})")
+
+    async def get_status(self, conn: DeviceConnection, remote_result_file: str) -> bool:
+        """True when the electron's result is readable (ssh.py:388-406)."""
+        entry = _inflight.get(remote_result_file)
+        return bool(entry and entry.staged is not None and entry.staged.batch.done
+                    and entry.staged.batch.error is None)
+
+    async def _poll_task(self, conn: DeviceConnection, remote_result_file: str, retries: int = 5) -> bool:
+        """Up to ``retries`` status checks, ``poll_freq`` seconds apart (ssh.py:408-432)."""
+        remaining = retries
+        while not await self.get_status(conn, remote_result_file):
+            if remaining == 1:
+                return False
+            await asyncio.sleep(self.poll_freq)
+            remaining -= 1
+        return True
+
+    async def query_result(self, conn: DeviceConnection, result_file: str,
+                           remote_result_file: str) -> Tuple[Any, Optional[Exception]]:
+        """``(result, exception)`` of the electron (ssh.py:434-458).  Device
+        callbacks cannot raise, so ``exception`` is always ``None`` here."""
+        entry = _inflight[remote_result_file]
+        return conn.engine.result_of(entry.staged), None
+
+    async def cleanup(
+        self,
+        conn: DeviceConnection,
+        function_file: str,
+        script_file: str,
+        result_file: str,
+        remote_function_file: str,
+        remote_script_file: str,
+        remote_result_file: str,
+    ) -> None:
+        """Drop the electron's book-keeping and its claim on the staging segment
+        (the six deletions of ssh.py:284-315)."""
+        entry = _inflight.pop(function_file, None)
+        _inflight.pop(remote_script_file, None)
+        _inflight.pop(remote_result_file, None)
+        if entry is not None and entry.staged is not None:
+            conn.engine.release(entry.staged)
+            entry.staged = None
+
+    async def cancel(self) -> bool:
+        """Unsupported, as in the reference (ssh.py:460-464)."""
+        raise NotImplementedError("Not implemented as it is unsupported for now")
+
+    # ------------------------------------------------------------------ run ---
+    async def run(self, function: Callable, args: list, kwargs: dict, task_metadata: Dict) -> Coroutine:
+        """Execute one electron and return its result (ssh.py:466-591)."""
+        dispatch_id = task_metadata["dispatch_id"]
+        node_id = task_metadata["node_id"]
+        operation_id = f"{dispatch_id}_{node_id}"
+        workdir = self.remote_workdir
+        if self.create_unique_workdir:
+            workdir = os.path.join(workdir, dispatch_id, f"node_{node_id}")
+
+        await self._validate_credentials()
+
+        connected, conn = await self._client_connect()
+        if not connected:
+            return self._on_ssh_fail(
+                function, args, kwargs,
+                f"Could not connect to host: '{self.hostname}' as user: '{self.username}'")
+
+        names = self._write_function_files(operation_id, function, args, kwargs, workdir)
+        function_file, script_file, remote_function_file, remote_script_file, remote_result_file = names
+        result_file = os.path.join(self.cache_dir, f"result_{operation_id}.pkl")
+        released = False
+        try:
+            await self._upload_task(conn, function_file, remote_function_file, script_file,
+                                    remote_script_file)
+            proc = await self.submit_task(conn, remote_script_file)
+            if proc.exit_status != 0:
+                message = proc.stderr.strip() or f"Task exited with nonzero exit status {proc.exit_status}."
+                app_log.warning(message)
+                return self._on_ssh_fail(function, args, kwargs, message)
+
+            if not await self._poll_task(conn, remote_result_file):
+                return self._on_ssh_fail(
+                    function, args, kwargs,
+                    f"Result file {remote_result_file} on remote host {self.hostname} was not found")
+
+            result, exception = await self.query_result(conn, result_file, remote_result_file)
+
+            if self.do_cleanup:
+                released = True
+                await self.cleanup(
+                    conn=conn,
+                    function_file=function_file,
+                    script_file=script_file,
+                    result_file=result_file,
+                    remote_function_file=remote_function_file,
+                    remote_script_file=remote_script_file,
+                    remote_result_file=remote_result_file,
+                )
+        finally:
+            if not released:
+                _forget(conn, function_file, remote_script_file, remote_result_file)
+
+        if exception is not None:
+            raise exception
+
+        conn.close()
+        await conn.wait_closed()
+        return result
+
+
+def _forget(conn, *names: str) -> None:
+    """Release staging state on failure paths and when ``do_cleanup`` is off (a
+    pinned segment must never stay claimed by an electron nobody will read)."""
+    entry = None
+    for n in names:
+        e = _inflight.pop(n, None)
+        entry = entry or e
+    if entry is not None and entry.staged is not None and isinstance(conn, DeviceConnection):
+        conn.engine.release(entry.staged)
+        entry.staged = None
+
+
+async def _open_engine(ordinal: int, hostname: str) -> DeviceConnection:
+    """Engine of one GPU as a connection object.  Translates "no such device /
+    device unusable" into ``ConnectionRefusedError`` so the caller's retry and
+    fallback policy applies; a missing library propagates untouched."""
+    try:
+        engine = get_engine(ordinal)
+    except _b2lib.LibraryMissing:
+        raise
+    except _b2lib.B2Error as err:
+        raise ConnectionRefusedError(f"GPU {ordinal} refused: {err}") from err
+    return DeviceConnection(engine, hostname)

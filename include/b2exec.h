@@ -1,0 +1,231 @@
+/*
+ * b2exec.h — C ABI of the B200 electron executor ("libb2exec.so").
+ *
+ * This is the drop-in boundary underneath the Python host
+ * (covalent_ssh_plugin_b200/ssh.py :: SSHExecutor).  The reference plugin has
+ * no FFI of its own: every step below is an asyncssh call in
+ * /root/reference/covalent_ssh_plugin/ssh.py.  Each entry point names the
+ * reference step it replaces (file:line).
+ *
+ *   reference step                                   replaced by
+ *   ------------------------------------------------ ---------------------------
+ *   asyncssh.connect + retry     ssh.py:237-282      b2_init / b2_peer_enable / b2_ipc_*
+ *   conn.close/wait_closed       ssh.py:585-587      b2_shutdown
+ *   pickle.dump -> function.pkl  ssh.py:147-150      host staging buffer (b2_host_buffer) + b2_task records
+ *   asyncssh.scp upload x2       ssh.py:360-361      b2_h2d  (+ b2_unpack into arg slots)
+ *   conn.run("python exec.py")   ssh.py:377-383      b2_enqueue + b2_launch  (worker kernel + callback table)
+ *   exec.py fn(*args, **kwargs)  exec.py:29-46       b2_register (callback table entry)
+ *   conn.run("ls result.pkl")    ssh.py:401-406      b2_poll / b2_wait
+ *   asyncssh.scp download        ssh.py:451          b2_pack of result slots + b2_d2h
+ *   rm x3                        ssh.py:313-315      arena offsets are simply reused by the host
+ *   (one dispatcher per host)    README.md:52-65     b2_peer_copy / b2_peer_pack over NVLink
+ *
+ * Conventions
+ *   - every function returns 0 (B2_OK) on success or a negative b2_err code;
+ *     b2_last_error() returns a thread-local, NUL-terminated description.
+ *   - plain C types only: pointers, sizes, fixed-width integers.  Python calls
+ *     these through ctypes (which releases the GIL for the duration).
+ *   - "dev" is a CUDA device ordinal.  All device memory is one arena per
+ *     device; every device address in this ABI is a BYTE OFFSET into that arena.
+ *   - the caller owns host buffers; the library owns the device arena, the
+ *     pinned staging buffers, streams, events and the device-side queue.
+ *   - work is stream-ordered per device: calls enqueue asynchronously on the
+ *     device's compute stream in call order; b2_sync / b2_wait / b2_poll are
+ *     the only blocking/observing calls.
+ */
+#ifndef B2EXEC_H
+#define B2EXEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1u
+
+/* ---- error codes -------------------------------------------------------- */
+enum b2_err {
+  B2_OK = 0,
+  B2_E_CUDA = -1,      /* a CUDA runtime call failed (text in b2_last_error) */
+  B2_E_ARG = -2,       /* bad argument (range, alignment, null)              */
+  B2_E_STATE = -3,     /* device not initialised / already initialised       */
+  B2_E_NOMEM = -4,     /* arena / staging / queue capacity exceeded          */
+  B2_E_NOTREADY = -5,  /* b2_poll: ticket not complete yet (not an error)    */
+  B2_E_UNSUPPORTED = -6
+};
+
+/* ---- per-electron status written by the worker kernel -------------------- */
+enum b2_task_status {
+  B2_TS_PENDING = 0,
+  B2_TS_OK = 1,
+  B2_TS_OVERFLOW = 2,  /* int64 electron overflowed: host must take the _on_ssh_fail path */
+  B2_TS_BAD_FN = 3,    /* fn_id has no callback registered                               */
+  B2_TS_BAD_ARG = 4    /* operand out of arena range / misaligned for the callback        */
+};
+
+/* ---- built-in callbacks (the on-device stand-in for exec.py:37) ---------- */
+enum b2_kind {
+  B2_K_NONE = 0,
+  B2_K_COPY = 1,       /* out[i]  = x[i]                     (bytes, count = bytes)   */
+  B2_K_SCALE_ADD = 2,  /* out[i]  = alpha * x[i] + beta      fp32, two roundings      */
+  B2_K_ADD = 3,        /* out[i]  = x[i] + y[i]              fp32                     */
+  B2_K_MUL = 4,        /* out[i]  = x[i] * y[i]              fp32                     */
+  B2_K_AXPY = 5,       /* out[i]  = alpha * x[i] + y[i]      fp32, two roundings      */
+  B2_K_SUM = 6,        /* out[0]  = sum_i x[i]               fp32 (tree order)        */
+  B2_K_STACK_SUM = 7,  /* out[i]  = ((x0[i]+x1[i])+x2[i])..  fp32, K rows, row order  */
+  B2_K_IADD = 8,       /* out[0]  = arg0 + arg1              int64 immediates, checked */
+  B2_K_IMUL = 9,       /* out[0]  = arg0 * arg1              int64 immediates, checked */
+  B2_K_ISCALE_ADD = 10,/* out[0]  = ialpha*arg0 + ibeta      int64, checked           */
+  B2_K__COUNT = 11
+};
+
+/* b2_task.flags */
+#define B2_F_IMM0 0x1u          /* arg0 is an immediate, not an arena offset   */
+#define B2_F_IMM1 0x2u          /* arg1 is an immediate                        */
+#define B2_F_ARENA0_SHIFT 8     /* bits 8..11 : arena id of arg0 (0 = local)   */
+#define B2_F_ARENA1_SHIFT 12    /* bits 12..15: arena id of arg1               */
+#define B2_F_ARENAO_SHIFT 16    /* bits 16..19: arena id of out                */
+#define B2_NO_SUCC 0xFFFFFFFFu
+#define B2_MAX_ARENAS 9         /* local + 8 peers                             */
+#define B2_MAX_FN 1024          /* callback-table capacity                     */
+
+/*
+ * One electron, as the worker kernel sees it (64 bytes, little endian).
+ * This record is the binary replacement of the pickled (fn, args, kwargs)
+ * tuple (ssh.py:150) for registered electrons: fn -> fn_id, ndarray args ->
+ * arena offsets of their raw buffers, Python ints -> immediates.
+ */
+typedef struct b2_task {
+  uint32_t fn_id;       /* callback-table index (b2_register)                    */
+  uint32_t flags;       /* B2_F_*                                                */
+  uint64_t arg0;        /* arena byte offset (16 B aligned) or immediate         */
+  uint64_t arg1;        /* second operand; for B2_K_STACK_SUM: row stride, bytes */
+  uint64_t out;         /* arena byte offset of the result (16 B aligned)        */
+  uint64_t count;       /* elements per operand (bytes for B2_K_COPY)            */
+  uint32_t nrows;       /* B2_K_STACK_SUM: number of stacked rows, else 0        */
+  uint32_t deps;        /* predecessors inside this batch still to finish        */
+  uint32_t succ_begin;  /* first index into the batch's successor list           */
+  uint32_t succ_count;  /* number of successors to release on completion         */
+  uint64_t tag;         /* opaque to the device; echoed nowhere (host bookkeeping) */
+} b2_task;
+
+/* One payload move for pack / unpack / peer routing (24 bytes). */
+typedef struct b2_span {
+  uint64_t src_off;     /* arena byte offset on the source device      */
+  uint64_t dst_off;     /* arena byte offset on the destination device */
+  uint64_t bytes;
+} b2_span;
+
+typedef struct b2_device_info {
+  int32_t  cc_major, cc_minor;
+  int32_t  sm_count;
+  int32_t  l2_bytes_mb;
+  uint64_t total_mem;
+  uint64_t arena_bytes;
+  uint64_t staging_in_bytes;
+  uint64_t staging_out_bytes;
+  uint32_t queue_cap;
+  uint32_t abi_version;
+  char     name[64];
+} b2_device_info;
+
+typedef struct b2_stats {
+  uint64_t launches_pack;     /* span-move launches (pack, unpack, peer_pack) */
+  uint64_t launches_worker;
+  uint64_t launches_other;    /* queue reset etc.                              */
+  uint64_t electrons;         /* tasks retired by the worker kernel           */
+  uint64_t bytes_packed;      /* sum of span bytes moved                      */
+  uint64_t bytes_h2d;
+  uint64_t bytes_d2h;
+} b2_stats;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+const char *b2_last_error(void);
+int b2_abi_version(void);
+int b2_device_count(int *count);
+
+/* Opens the "connection" to one GPU (replaces asyncssh.connect, ssh.py:263-268):
+ * creates streams, allocates the device arena, two pinned host staging buffers
+ * (ingress = host->device, egress = device->host), the task table and the MPMC
+ * queue (queue_cap cells, power of two), and installs the built-in callbacks. */
+int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes,
+            uint64_t staging_out_bytes, uint32_t queue_cap);
+int b2_shutdown(int dev);                       /* ssh.py:585-587 */
+int b2_is_initialized(int dev);
+int b2_get_info(int dev, b2_device_info *out);
+int b2_get_stats(int dev, b2_stats *out);
+
+/* ---- memory -------------------------------------------------------------- */
+/* which: 0 = ingress (pinned, host writes / device reads), 1 = egress. */
+int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes);
+/* async copies on the device's compute stream; host_off is relative to the
+ * pinned staging buffer named by the direction (ssh.py:360-361 / ssh.py:451). */
+int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes);
+int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes);
+/* synchronous debug/test helpers for arbitrary (pageable) host memory */
+int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes);
+int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes);
+int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes);
+
+/* ---- pack / unpack (K1 / K2) --------------------------------------------- */
+/* Generic span move inside one arena: for every i, arena[dst_off .. +bytes)
+ * = arena[src_off .. +bytes).  Spans must not overlap each other's
+ * destinations.  Fast path needs 16 B aligned offsets; any alignment works. */
+int b2_move_spans(int dev, const b2_span *spans, uint32_t n);
+/* pack: gather n scattered payloads into one contiguous run starting at
+ * dst_off; payload i lands at dst_off + prefix(round_up(bytes, align)).
+ * unpack: the inverse (contiguous source, scattered destinations).
+ * If out_offs != NULL it receives the n contiguous-side offsets. */
+int b2_pack(int dev, const uint64_t *src_offs, const uint64_t *sizes, uint32_t n,
+            uint64_t dst_off, uint32_t align, uint64_t *out_offs, uint64_t *out_total);
+int b2_unpack(int dev, uint64_t src_off, const uint64_t *dst_offs, const uint64_t *sizes,
+              uint32_t n, uint32_t align, uint64_t *out_offs, uint64_t *out_total);
+
+/* ---- callback table + queue (K3) ----------------------------------------- */
+/* Binds fn_id to a built-in callback and its registered constants; the
+ * on-device replacement of "unpickle fn" (exec.py:29-30). */
+int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta,
+                int64_t ialpha, int64_t ibeta);
+/* Appends n electrons (and their successor list) to the device's pending
+ * batch.  succ may be NULL when no task has successors.  Returns the index of
+ * the first appended task in *first_index (successor indices are batch-relative). */
+int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ,
+               uint32_t n_succ, uint32_t *first_index);
+/* Uploads the pending batch's task table, pushes ready electrons into the
+ * device MPMC queue and runs the persistent worker kernel until every electron
+ * of the batch has retired.  status_host_off: egress offset that receives one
+ * uint32 b2_task_status per electron (pass UINT64_MAX to skip the copy).
+ * Returns a ticket for b2_poll / b2_wait. */
+int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket);
+/* Records a completion ticket after whatever has been queued so far. */
+int b2_mark(int dev, uint64_t *ticket);
+int b2_poll(int dev, uint64_t ticket);          /* B2_OK | B2_E_NOTREADY  (ssh.py:388-406) */
+int b2_wait(int dev, uint64_t ticket);          /* blocks (ssh.py:408-432) */
+int b2_sync(int dev);
+
+/* ---- inter-GPU routing (K4) ---------------------------------------------- */
+/* same-process peers */
+int b2_peer_enable(int dev, int peer_dev, uint32_t *arena_id);
+/* cross-process peers (one process per GPU under torchrun): export this
+ * device's arena as a 64-byte CUDA IPC handle, map a peer's handle. */
+int b2_ipc_export(int dev, void *handle64);
+int b2_ipc_open(int dev, const void *handle64, uint64_t peer_arena_bytes, uint32_t *arena_id);
+/* copy engine path (cudaMemcpyPeerAsync) and kernel path (remote stores). */
+int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_off, uint64_t bytes);
+int b2_peer_pack(int dev, uint32_t dst_arena_id, const b2_span *spans, uint32_t n);
+
+/* ---- measurement --------------------------------------------------------- */
+/* CUDA events on the device's compute stream (the stream every kernel of this
+ * library is launched on). */
+int b2_event_create(int dev, uint32_t *event_id);
+int b2_event_record(int dev, uint32_t event_id);
+int b2_event_elapsed_ms(int dev, uint32_t start_id, uint32_t stop_id, float *ms);
+/* writes arena[off .. off+bytes) with a rolling pattern; used to evict L2. */
+int b2_flush_l2(int dev, uint64_t scratch_off, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2EXEC_H */
