@@ -60,6 +60,18 @@ def is_fresh() -> bool:
     )
 
 
+def build_variant(out: Path, defines: dict) -> Path:
+    """Tuning builds (tools/sweep.py): same sources with -D overrides, written to
+    ``out`` and selected at run time with B2EXEC_LIB=<out>."""
+    out.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-o", str(out)]
+    cmd += [str(CSRC / s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into libb2exec.so unless it is already up to date."""
     if not force and is_fresh():

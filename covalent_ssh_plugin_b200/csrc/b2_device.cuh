@@ -10,7 +10,8 @@ namespace b2 {
 
 constexpr int kWarp = 32;
 constexpr int kMoveThreads = 256;          // 8 warps per CTA in the span mover
-constexpr int kWorkerThreads = 256;        // 8 warps per CTA in the worker
+constexpr int kWorkerThreads = 256;        // 8 worker warps per CTA in the worker kernel
+constexpr int kCtaThreads = kWorkerThreads + kWarp;   // + 1 scheduler warp
 constexpr uint32_t kChunkBytes = 16384;    // one warp work unit in the span mover
 
 // ---- streaming 128-bit accessors ------------------------------------------
@@ -73,16 +74,25 @@ struct FnEntry {
   long long ialpha, ibeta;
 };
 
-// MPMC queue of ready electrons.  A cell packs (seq << 32) | task_index so a
-// single 64-bit release store publishes both.  For ticket t (cell t & mask):
-//   seq == t      : free, producer with ticket t may fill it
-//   seq == t + 1  : full, consumer at head == t may take it
-// after consumption the cell is re-armed with seq = t + cap.
+// MPMC queue of ready electrons (bounded: one launch never enqueues more than
+// cap electrons, and every electron is enqueued exactly once per launch).
+// Producers and consumers both take tickets with one fetch-add, so neither
+// side retries under contention:
+//   producer: t = P + tail++ ; cells[t] = (epoch << 32) | task_index  (release)
+//   consumer: t = head++ ; if t >= n_tasks -> nothing left for this CTA, leave
+//             if t < P   -> task t itself (the ready prefix bypasses the cells)
+//             spin until cells[t] >> 32 == epoch                      (acquire)
+// A ticket below n_tasks is always filled eventually, because exactly n_tasks
+// pushes happen per launch; tickets are handed out in order, so every filled
+// cell already has an owner that is running it (no lost wake-ups, no waiting
+// on a CTA that has not been scheduled).  The last CTA to leave zeroes
+// head/tail/cursor; the host bumps the epoch per launch, which is what makes
+// stale cells from earlier launches unreadable.
 struct Queue {
   unsigned long long *cells;
-  uint32_t *head;                // consumer ticket (CAS)
+  uint32_t *head;                // consumer ticket (fetch-add)
   uint32_t *tail;                // producer ticket (fetch-add)
-  unsigned long long *retired;   // electrons retired since init (monotonic)
+  uint32_t epoch;                // launch number, >= 1
   uint32_t mask;                 // cap - 1
 };
 
@@ -99,9 +109,10 @@ struct WorkerArgs {
   uint32_t *status;              // one b2_task_status per electron
   const FnEntry *fn_table;
   Queue q;
-  uint32_t *cursor;              // claim cursor over the task table (zeroed before each launch)
+  uint32_t *cursor;              // claim cursor over tasks [n_ready_prefix, n_tasks)
+  uint32_t *exited;              // CTAs that have left; the last one re-arms the counters
   uint32_t n_tasks;
-  unsigned long long retire_target;   // stop when *q.retired reaches this
+  uint32_t n_ready_prefix;       // tasks [0, P) are ready at submit: ticket t < P runs task t
   uint8_t *arena[B2_MAX_ARENAS];
   uint64_t arena_bytes[B2_MAX_ARENAS];
 };

@@ -14,18 +14,10 @@
 namespace b2 {
 
 // ------------------------------------------------------------------ queue ---
-__device__ __forceinline__ void queue_push(const Queue &q, uint32_t task_index) {
-  const uint32_t t = atomicAdd(q.tail, 1u);
-  unsigned long long *cell = q.cells + (t & q.mask);
-  // The host never lets more than cap electrons be outstanding, so the cell is
-  // free already; the wait only guards the wrap-around window.
-  while ((uint32_t)(ld_acquire_u64(cell) >> 32) != t) __nanosleep(64);
-  st_release_u64(cell, ((unsigned long long)(t + 1u) << 32) | task_index);
-}
-
 // Warp-aggregated push: lanes with want != 0 each enqueue one index with a
-// single fetch-add on the tail per warp.
-__device__ __forceinline__ void queue_push_warp(const Queue &q, bool want, uint32_t task_index) {
+// single fetch-add on the tail per warp.  Must be called by all 32 lanes.
+__device__ __forceinline__ void queue_push_warp(const Queue &q, uint32_t first_ticket, bool want,
+                                                uint32_t task_index) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
   if (m == 0) return;
   const int lane = threadIdx.x & 31;
@@ -34,38 +26,35 @@ __device__ __forceinline__ void queue_push_warp(const Queue &q, bool want, uint3
   if (lane == leader) base = atomicAdd(q.tail, (uint32_t)__popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
   if (want) {
-    const uint32_t t = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-    unsigned long long *cell = q.cells + (t & q.mask);
-    while ((uint32_t)(ld_acquire_u64(cell) >> 32) != t) __nanosleep(64);
-    st_release_u64(cell, ((unsigned long long)(t + 1u) << 32) | task_index);
+    const uint32_t t = first_ticket + base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    st_release_u64(q.cells + (t & q.mask), ((unsigned long long)q.epoch << 32) | task_index);
   }
 }
 
 constexpr uint32_t kNoTask = 0xFFFFFFFFu;
 
-// One thread per CTA.  Returns kNoTask once every electron of the batch has
-// retired.
-__device__ __forceinline__ uint32_t queue_pop(const Queue &q, unsigned long long retire_target) {
-  uint32_t backoff = 32;
+// One thread per CTA: claim the next ticket.
+__device__ __forceinline__ uint32_t queue_claim(const Queue &q) { return atomicAdd(q.head, 1u); }
+
+// One thread per CTA: wait until the claimed ticket has been published.
+__device__ __forceinline__ uint32_t queue_take(const Queue &q, uint32_t ticket, uint32_t n_tasks) {
+  if (ticket >= n_tasks) return kNoTask;
+  const unsigned long long *cell = q.cells + (ticket & q.mask);
+  uint32_t backoff = 20;
   for (;;) {
-    const uint32_t h = ld_relaxed_u32(q.head);
-    unsigned long long *cell = q.cells + (h & q.mask);
     const unsigned long long v = ld_acquire_u64(cell);
-    if ((uint32_t)(v >> 32) == h + 1u) {
-      if (atomicCAS(q.head, h, h + 1u) == h) {
-        st_release_u64(cell, (unsigned long long)(h + q.mask + 1u) << 32);
-        return (uint32_t)v;
-      }
-      continue;  // lost the race for this cell; look at the new head
-    }
-    // Empty (or head moved under us).  Leave only when the batch is finished.
-    if (ld_acquire_u64(q.retired) >= retire_target) return kNoTask;
+    if ((uint32_t)(v >> 32) == q.epoch) return (uint32_t)v;
     __nanosleep(backoff);
-    if (backoff < 1024) backoff <<= 1;
+    if (backoff < 640) backoff <<= 1;
   }
 }
 
 // -------------------------------------------------------------- callbacks ---
+// Barrier over the 8 worker warps only (the scheduler warp never joins it).
+__device__ __forceinline__ void worker_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory");
+}
+
 struct Ctx {
   const uint8_t *a0;     // operand 0 (nullptr when immediate)
   const uint8_t *a1;     // operand 1
@@ -77,7 +66,13 @@ struct Ctx {
 };
 typedef uint32_t (*callback_t)(const Ctx &);   // returns a b2_task_status; called by all threads
 
-constexpr int kVec = 4;  // 128-bit vectors in flight per thread
+#ifndef B2_WORKER_VEC
+#define B2_WORKER_VEC 4
+#endif
+#ifndef B2_WORKER_MIN_CTAS
+#define B2_WORKER_MIN_CTAS 4
+#endif
+constexpr int kVec = B2_WORKER_VEC;  // 128-bit vectors in flight per thread
 
 template <typename F>
 __device__ __forceinline__ void cta_map1(const Ctx &c, F f) {
@@ -214,7 +209,7 @@ __device__ uint32_t cb_sum(const Ctx &c) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
-  __syncthreads();
+  worker_sync();
   if (threadIdx.x == 0) {
     double s = 0.0;
 #pragma unroll
@@ -328,114 +323,170 @@ __device__ __forceinline__ uint8_t *resolve(const WorkerArgs &a, uint32_t arena_
   return a.arena[arena_id] + off;
 }
 
-__global__ void __launch_bounds__(kWorkerThreads)
+// Named barriers (barrier 0 is __syncthreads over the whole CTA, barrier 1 is
+// worker_sync over the 8 worker warps).
+enum : int { kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
+__device__ __forceinline__ void bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// What the scheduler warp hands to the worker warps through shared memory.
+struct Slot {
+  b2_task t;
+  FnEntry fn;
+  uint32_t index;   // task index, or kNoTask: nothing left for this CTA
+  uint32_t kind;    // validated b2_kind, or B2_K__COUNT for "bad fn_id"
+};
+
+// One CTA = 8 worker warps + 1 scheduler warp.  The scheduler runs one electron
+// ahead: while the workers stream electron k it claims the next ticket, waits
+// for that cell to be published if it is a released dependent, and stages the
+// task record and its callback-table entry in shared memory, so the L2 round
+// trips of fetching work never sit between two electrons.
+__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_kernel(const __grid_constant__ WorkerArgs a) {
-  __shared__ uint32_t s_task;
+  __shared__ Slot slots[2];
+  __shared__ uint32_t s_base;
   __shared__ uint32_t s_status;
+  const uint32_t P = a.n_ready_prefix;
 
-  // Prologue: publish the electrons that are ready at submit time (deps == 0).
-  // Blocks of 256 task indices are claimed through a cursor, so whichever CTAs
-  // are resident do all of the publishing (no CTA waits on one that has not
-  // been scheduled yet) and CTAs that find the cursor exhausted go straight to
-  // consuming while others are still producing.
-  for (;;) {
-    if (threadIdx.x == 0) s_task = atomicAdd(a.cursor, (uint32_t)kWorkerThreads);
-    __syncthreads();
-    const uint32_t base = s_task;
-    __syncthreads();
-    if (base >= a.n_tasks) break;
-    const uint32_t i = base + threadIdx.x;
-    const bool ready = (i < a.n_tasks) && (a.tasks[i].deps == 0);
-    queue_push_warp(a.q, ready, i);
-  }
+  if (threadIdx.x >= kWorkerThreads) {
+    // ------------------------------------------------------- scheduler warp --
+    const int lane = threadIdx.x & 31;
+    uint32_t k = 0;
+    for (;; ++k) {
+      const int s = k & 1;
+      if (k >= 2) bar_sync(kBarEmpty0 + s, kCtaThreads);   // workers are done with this slot
+      uint32_t ti = kNoTask;
+      if (lane == 0) {
+        const uint32_t ticket = queue_claim(a.q);
+        // Tickets below the ready prefix ARE task indices: electrons that are
+        // ready at submit never touch the queue cells.
+        ti = (ticket < P) ? ticket : queue_take(a.q, ticket, a.n_tasks);
+        Slot &sl = slots[s];
+        sl.index = ti;
+        if (ti != kNoTask) {
+          sl.t = a.tasks[ti];
+          uint32_t kind = B2_K__COUNT;
+          if (sl.t.fn_id < B2_MAX_FN) {
+            sl.fn = a.fn_table[sl.t.fn_id];
+            kind = sl.fn.kind;
+            if (kind >= B2_K__COUNT || (kind == B2_K_NONE && sl.t.fn_id != 0)) kind = B2_K__COUNT;
+          }
+          sl.kind = kind;
+        }
+        __threadfence_block();
+      }
+      ti = __shfl_sync(0xffffffffu, ti, 0);
+      bar_arrive(kBarFull0 + s, kCtaThreads);
+      if (ti == kNoTask) break;
+    }
+    // drain the arrivals the workers posted for slots that are never refilled
+    if (k >= 1) bar_sync(kBarEmpty0 + ((k - 1) & 1), kCtaThreads);
+  } else {
+    // --------------------------------------------------------- worker warps --
+    // Electrons that are ready at submit but sit behind a dependent one in the
+    // table (index >= P) are published here; blocks of 256 indices are claimed
+    // through a cursor so that whichever CTAs are resident do all of it.
+    if (P < a.n_tasks) {
+      for (;;) {
+        if (threadIdx.x == 0) s_base = P + atomicAdd(a.cursor, (uint32_t)kWorkerThreads);
+        worker_sync();
+        const uint32_t base = s_base;
+        worker_sync();
+        if (base >= a.n_tasks) break;
+        const uint32_t i = base + threadIdx.x;
+        const bool ready = (i < a.n_tasks) && (a.tasks[i].deps == 0);
+        queue_push_warp(a.q, P, ready, i);
+      }
+    }
 
-  for (;;) {
-    if (threadIdx.x == 0) s_task = queue_pop(a.q, a.retire_target);
-    __syncthreads();
-    const uint32_t ti = s_task;
-    if (ti == kNoTask) break;
-
-    const b2_task t = a.tasks[ti];  // 64 B, same for every thread (L1 broadcast)
-    uint32_t status;
-    if (t.fn_id >= B2_MAX_FN) {
-      status = B2_TS_BAD_FN;
-    } else {
-      const FnEntry *fn = a.fn_table + t.fn_id;
-      const uint32_t kind = fn->kind;
-      if (kind == B2_K_NONE && t.fn_id != 0) {
-        status = B2_TS_BAD_FN;
-      } else if (kind >= B2_K__COUNT) {
+    for (uint32_t k = 0;; ++k) {
+      const int s = k & 1;
+      bar_sync(kBarFull0 + s, kCtaThreads);
+      const Slot &sl = slots[s];
+      const uint32_t ti = sl.index;
+      if (ti == kNoTask) break;
+      const uint32_t kind = sl.kind;
+      uint32_t status;
+      if (kind >= B2_K__COUNT) {
         status = B2_TS_BAD_FN;
       } else {
         Ctx c;
         bool ok = true;
+        const uint64_t arg0 = sl.t.arg0, arg1 = sl.t.arg1, count = sl.t.count;
+        const uint32_t flags = sl.t.flags, nrows = sl.t.nrows;
         const uint64_t esz = (kind == B2_K_COPY) ? 1 : 4;  // bytes per element of array operands
         const bool is_int = (kind == B2_K_IADD || kind == B2_K_IMUL || kind == B2_K_ISCALE_ADD);
-        uint64_t in_bytes = t.count * esz;
-        if (kind == B2_K_STACK_SUM && t.nrows) in_bytes += (uint64_t)(t.nrows - 1) * t.arg1;
-        uint64_t out_bytes = (kind == B2_K_SUM) ? 4 : (is_int ? 8 : t.count * esz);
-        c.imm0 = t.arg0;
-        c.imm1 = t.arg1;
-        c.a0 = (t.flags & B2_F_IMM0 || is_int || kind == B2_K_NONE)
+        uint64_t in_bytes = count * esz;
+        if (kind == B2_K_STACK_SUM && nrows) in_bytes += (uint64_t)(nrows - 1) * arg1;
+        const uint64_t out_bytes = (kind == B2_K_SUM) ? 4 : (is_int ? 8 : count * esz);
+        c.imm0 = arg0;
+        c.imm1 = arg1;
+        c.a0 = ((flags & B2_F_IMM0) || is_int || kind == B2_K_NONE)
                    ? nullptr
-                   : resolve(a, (t.flags >> B2_F_ARENA0_SHIFT) & 15u, t.arg0, in_bytes, &ok);
+                   : resolve(a, (flags >> B2_F_ARENA0_SHIFT) & 15u, arg0, in_bytes, &ok);
         const bool two = (kind == B2_K_ADD || kind == B2_K_MUL || kind == B2_K_AXPY);
-        c.a1 = (two && !(t.flags & B2_F_IMM1))
-                   ? resolve(a, (t.flags >> B2_F_ARENA1_SHIFT) & 15u, t.arg1, in_bytes, &ok)
+        c.a1 = (two && !(flags & B2_F_IMM1))
+                   ? resolve(a, (flags >> B2_F_ARENA1_SHIFT) & 15u, arg1, in_bytes, &ok)
                    : nullptr;
         c.out = (kind == B2_K_NONE)
                     ? nullptr
-                    : resolve(a, (t.flags >> B2_F_ARENAO_SHIFT) & 15u, t.out, out_bytes, &ok);
-        c.count = t.count;
-        c.nrows = t.nrows;
-        c.fn = fn;
+                    : resolve(a, (flags >> B2_F_ARENAO_SHIFT) & 15u, sl.t.out, out_bytes, &ok);
+        c.count = count;
+        c.nrows = nrows;
+        c.fn = &sl.fn;
         status = ok ? g_callbacks[kind](c) : (uint32_t)B2_TS_BAD_ARG;
       }
-    }
-    if (threadIdx.x == 0) s_status = status;
-    __syncthreads();  // all result stores of this CTA are ordered before thread 0's fence below
+      const uint32_t succ_begin = sl.t.succ_begin, succ_count = sl.t.succ_count;
+      if (threadIdx.x == 0) s_status = status;
+      worker_sync();  // every result store of this CTA is ordered before what follows
 
-    if (threadIdx.x == 0) {
-      a.status[ti] = s_status;
-      __threadfence();  // results + status visible device-wide before successors are released
-    }
-    // Release successors: one lane per successor edge.  Each releasing lane
-    // fences first: the barrier above ordered the whole CTA's result stores
-    // before it, the fence makes them visible device-wide before the decrement
-    // another SM may observe.
-    if (t.succ_count) {
-      for (uint32_t base = 0; base < t.succ_count; base += kWorkerThreads) {
+      if (threadIdx.x == 0) a.status[ti] = s_status;
+      // Release successors, one lane per edge.  Each releasing lane fences first:
+      // the barrier above ordered the whole CTA's result stores before it, the
+      // fence makes them visible device-wide before the decrement another SM
+      // may observe.
+      for (uint32_t base = 0; base < succ_count; base += kWorkerThreads) {
         const uint32_t e = base + threadIdx.x;
         bool fire = false;
         uint32_t sidx = 0;
-        if (e < t.succ_count) {
-          sidx = a.succ[t.succ_begin + e];
+        if (e < succ_count) {
+          sidx = a.succ[succ_begin + e];
           if (sidx < a.n_tasks) {
             __threadfence();
             fire = (atomicSub(&a.tasks[sidx].deps, 1u) == kDepBias + 1u);
           }
         }
-        queue_push_warp(a.q, fire, sidx);
+        queue_push_warp(a.q, P, fire, sidx);
       }
+      __threadfence_block();
+      bar_arrive(kBarEmpty0 + s, kCtaThreads);  // the scheduler may refill this slot
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  }
+
+  // Last CTA out re-arms the counters for the next launch (no memset node).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.exited, 1u) == gridDim.x - 1) {
+      *a.q.head = 0;
+      *a.q.tail = 0;
+      *a.cursor = 0;
+      *a.exited = 0;
       __threadfence();
-      atomicAdd(a.q.retired, 1ull);
     }
   }
 }
 
-// Re-arms the queue cells once at init: cell i is free for ticket i.
-__global__ void queue_init_kernel(unsigned long long *cells, uint32_t cap, uint32_t *head,
-                                  uint32_t *tail, unsigned long long *retired) {
+// Zeroes the queue cells once at init (epoch 0 is never used by a launch).
+__global__ void queue_init_kernel(unsigned long long *cells, uint32_t cap, uint32_t *counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap) cells[i] = (unsigned long long)i << 32;
-  if (i == 0) {
-    *head = 0;
-    *tail = 0;
-    *retired = 0;
-  }
+  if (i < cap) cells[i] = 0ull;
+  if (i < 64) counters[i] = 0u;
 }
 
 }  // namespace b2

@@ -60,7 +60,8 @@ struct Staging {
   uint8_t *h = nullptr;
   uint8_t *d = nullptr;
   size_t cap = 0;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr;   // last consumer of this slot has finished
+  cudaEvent_t up = nullptr;   // upload of this slot has finished (task tables)
   bool in_flight = false;
 };
 
@@ -69,7 +70,8 @@ struct Device {
   bool up = false;
   int dev = -1;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;         // compute: every kernel and payload copy, in call order
+  cudaStream_t upload = nullptr;         // task tables only, so table k+1 uploads while kernel k runs
 
   uint8_t *h_in = nullptr, *h_out = nullptr;
   uint64_t h_in_bytes = 0, h_out_bytes = 0;
@@ -83,10 +85,9 @@ struct Device {
 
   // queue + callback table
   unsigned long long *d_cells = nullptr;
-  uint32_t *d_head = nullptr, *d_tail = nullptr, *d_cursor = nullptr;
-  unsigned long long *d_retired = nullptr;
+  uint32_t *d_head = nullptr, *d_tail = nullptr, *d_cursor = nullptr, *d_exited = nullptr;
   uint32_t qcap = 0;
-  unsigned long long retired_total = 0;
+  uint32_t epoch = 0;
   FnEntry *d_fn = nullptr;
   uint32_t *d_status = nullptr;
 
@@ -94,6 +95,8 @@ struct Device {
   Staging task_ring[kRing];
   int task_slot = 0;
   uint32_t pend_tasks = 0, pend_succ = 0, succ_cap = 0;
+  uint32_t pend_prefix = 0;      // leading electrons with deps == 0
+  bool pend_prefix_open = true;
 
   Staging span_ring[kRing];
   int span_slot = 0;
@@ -149,6 +152,7 @@ void staging_free(Staging &s) {
   if (s.h) cudaFreeHost(s.h);
   if (s.d) cudaFree(s.d);
   if (s.ev) cudaEventDestroy(s.ev);
+  if (s.up) cudaEventDestroy(s.up);
   s = Staging();
 }
 
@@ -205,8 +209,6 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   if (chunks == 0) return B2_OK;
 
   CU(cudaMemcpyAsync(s.d, s.h, total, cudaMemcpyHostToDevice, D->stream));
-  CU(cudaEventRecord(s.ev, D->stream));
-  s.in_flight = true;
 
   const uint32_t cps = uniform ? (uint32_t)((b0 + kChunkBytes - 1) / kChunkBytes) : 0u;
   const int warps_per_cta = kMoveThreads / kWarp;
@@ -221,6 +223,8 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
     default: launch_mover<8>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
   }
   CU(cudaGetLastError());
+  CU(cudaEventRecord(s.ev, D->stream));
+  s.in_flight = true;
   D->stats.launches_pack += 1;
   D->stats.bytes_packed += moved;
   return B2_OK;
@@ -281,6 +285,7 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   D->dev = dev;
   D->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&D->upload, cudaStreamNonBlocking));
 
   CU(cudaMalloc(reinterpret_cast<void **>(&D->arena[0]), arena_bytes));
   D->arena_bytes[0] = arena_bytes;
@@ -302,24 +307,25 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_head), 256));
   D->d_tail = D->d_head + 16;     // separate 64 B sectors
   D->d_cursor = D->d_head + 32;
-  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_retired), 64));
+  D->d_exited = D->d_head + 48;
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_fn), sizeof(FnEntry) * B2_MAX_FN));
   CU(cudaMemsetAsync(D->d_fn, 0, sizeof(FnEntry) * B2_MAX_FN, D->stream));
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_status), (size_t)queue_cap * 4));
   queue_init_kernel<<<(queue_cap + 255) / 256, 256, 0, D->stream>>>(D->d_cells, queue_cap,
-                                                                   D->d_head, D->d_tail,
-                                                                   D->d_retired);
+                                                                   D->d_head);
   CU(cudaGetLastError());
   D->stats = b2_stats();
   D->stats.launches_other = 1;
-  D->retired_total = 0;
+  D->epoch = 0;
   D->pend_tasks = D->pend_succ = 0;
+  D->pend_prefix = 0;
+  D->pend_prefix_open = true;
   D->task_slot = D->span_slot = 0;
   D->next_ticket = 1;
   D->n_user_ev = 0;
 
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_kernel,
-                                                   kWorkerThreads, 0));
+                                                   kCtaThreads, 0));
   D->mover_unroll = env_int("B2_MOVER_UNROLL", 8);
   if (D->mover_unroll != 4 && D->mover_unroll != 16) D->mover_unroll = 8;
   switch (D->mover_unroll) {
@@ -340,8 +346,18 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   const int mcap = env_int("B2_MOVER_CTAS_PER_SM", 0);
   if (mcap > 0) D->mover_ctas_per_sm = std::min(D->mover_ctas_per_sm, mcap);
 
-  // gate electron: fn_id 0 is a registered no-op (kind NONE) used to fan a
-  // dependency out to many successors.
+  // Size every staging slot up front so that steady-state calls never allocate
+  // (cudaHostAlloc / cudaMalloc synchronise the device).
+  for (auto &s : D->task_ring) {
+    int rc = staging_reserve(s, (size_t)queue_cap * sizeof(b2_task) + (size_t)D->succ_cap * 4);
+    if (rc) return rc;
+  }
+  for (auto &s : D->span_ring) {
+    int rc = staging_reserve(s, (size_t)1 << 20);
+    if (rc) return rc;
+  }
+  // fn_id 0 stays kind NONE: the gate electron, a registered no-op used to fan
+  // one dependency out to many successors.
   CU(cudaStreamSynchronize(D->stream));
   D->up = true;
   return B2_OK;
@@ -353,6 +369,7 @@ int b2_shutdown(int dev) {
   std::lock_guard<std::mutex> lock_(D->mu);
   if (!D->up) return fail(B2_E_STATE, "device %d is not initialised", dev);
   cudaSetDevice(dev);
+  cudaStreamSynchronize(D->upload);
   cudaStreamSynchronize(D->stream);
   for (int i = 1; i < D->n_arenas; ++i)
     if (D->arena_ipc[i] && D->arena[i]) cudaIpcCloseMemHandle(D->arena[i]);
@@ -367,10 +384,10 @@ int b2_shutdown(int dev) {
   if (D->h_out) cudaFreeHost(D->h_out);
   cudaFree(D->d_cells);
   cudaFree(D->d_head);
-  cudaFree(D->d_retired);
   cudaFree(D->d_fn);
   cudaFree(D->d_status);
   cudaStreamDestroy(D->stream);
+  cudaStreamDestroy(D->upload);
   for (int i = 0; i < B2_MAX_ARENAS; ++i) {
     D->arena[i] = nullptr;
     D->arena_bytes[i] = 0;
@@ -420,6 +437,20 @@ int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes) {
   } else if (which == 1) {
     *ptr = D->h_out;
     *bytes = D->h_out_bytes;
+  } else {
+    return fail(B2_E_ARG, "which must be 0 (ingress) or 1 (egress)");
+  }
+  return B2_OK;
+}
+
+int b2_detach_host_buffer(int dev, int which) {
+  DEV_OR_FAIL(D, dev);
+  if (which == 0) {
+    D->h_in = nullptr;
+    D->h_in_bytes = 0;
+  } else if (which == 1) {
+    D->h_out = nullptr;
+    D->h_out_bytes = 0;
   } else {
     return fail(B2_E_ARG, "which must be 0 (ingress) or 1 (egress)");
   }
@@ -582,6 +613,12 @@ int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, 
       ht[i].deps += kDepBias;  // see kDepBias in b2_device.cuh
     }
   }
+  for (uint32_t i = 0; i < n && D->pend_prefix_open; ++i) {
+    if (ht[i].deps == 0)
+      D->pend_prefix += 1;
+    else
+      D->pend_prefix_open = false;
+  }
   if (n_succ)
     memcpy(reinterpret_cast<uint32_t *>(s.h + succ_off) + D->pend_succ, succ, (size_t)n_succ * 4);
   D->pend_tasks += n;
@@ -608,13 +645,15 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
                 (unsigned long long)status_host_off, n);
   Staging &s = D->task_ring[D->task_slot];
   const size_t succ_off = (size_t)D->qcap * sizeof(b2_task);
-  CU(cudaMemcpyAsync(s.d, s.h, (size_t)n * sizeof(b2_task), cudaMemcpyHostToDevice, D->stream));
+  // The table travels on its own stream: the upload for this launch overlaps
+  // whatever the compute stream is still running; the kernel waits for it.
+  if (!s.up) CU(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
+  CU(cudaMemcpyAsync(s.d, s.h, (size_t)n * sizeof(b2_task), cudaMemcpyHostToDevice, D->upload));
   if (D->pend_succ)
     CU(cudaMemcpyAsync(s.d + succ_off, s.h + succ_off, (size_t)D->pend_succ * 4,
-                       cudaMemcpyHostToDevice, D->stream));
-  CU(cudaEventRecord(s.ev, D->stream));
-  s.in_flight = true;
-  CU(cudaMemsetAsync(D->d_cursor, 0, 4, D->stream));
+                       cudaMemcpyHostToDevice, D->upload));
+  CU(cudaEventRecord(s.up, D->upload));
+  CU(cudaStreamWaitEvent(D->stream, s.up, 0));
 
   WorkerArgs a;
   memset(&a, 0, sizeof a);
@@ -625,20 +664,24 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   a.q.cells = D->d_cells;
   a.q.head = D->d_head;
   a.q.tail = D->d_tail;
-  a.q.retired = D->d_retired;
+  if (++D->epoch == 0) D->epoch = 1;
+  a.q.epoch = D->epoch;
   a.q.mask = D->qcap - 1;
   a.cursor = D->d_cursor;
+  a.exited = D->d_exited;
   a.n_tasks = n;
-  D->retired_total += n;
-  a.retire_target = D->retired_total;
+  a.n_ready_prefix = D->pend_prefix;
   for (int i = 0; i < B2_MAX_ARENAS; ++i) {
     a.arena[i] = D->arena[i];
     a.arena_bytes[i] = D->arena_bytes[i];
   }
   const int cap = D->sm_count * std::max(1, D->worker_ctas_per_sm);
   const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
-  worker_kernel<<<grid, kWorkerThreads, 0, D->stream>>>(a);
+  worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
   CU(cudaGetLastError());
+  // the slot (pinned table + device mirror) is reusable once this kernel is done
+  CU(cudaEventRecord(s.ev, D->stream));
+  s.in_flight = true;
   D->stats.launches_worker += 1;
   D->stats.electrons += n;
   if (status_host_off != UINT64_MAX) {
@@ -649,6 +692,8 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
   D->task_slot = (D->task_slot + 1) % kRing;
   D->pend_tasks = D->pend_succ = 0;
+  D->pend_prefix = 0;
+  D->pend_prefix_open = true;
   return record_ticket(D, ticket);
 }
 

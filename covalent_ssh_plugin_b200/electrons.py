@@ -174,6 +174,8 @@ def _as_operand(x: Any) -> Tuple[np.ndarray, tuple, str]:
     """(flat uint8 view of the raw buffer, shape, order) of a float32 ndarray."""
     if type(x) is not np.ndarray or x.dtype != np.float32:
         raise NotDeviceEligible("array operands must be float32 numpy.ndarray")
+    if x.ndim == 0:
+        raise NotDeviceEligible("0-d arrays behave like numpy scalars on the host")
     if x.flags.c_contiguous:
         order = "C"
     elif x.flags.f_contiguous:

@@ -28,6 +28,7 @@ import os
 import queue
 import struct
 import threading
+import weakref
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -45,8 +46,10 @@ DEFAULTS = {
     "arena_bytes": int(os.environ.get("B2_ARENA_BYTES", 4096 * MiB)),
     "staging_bytes": int(os.environ.get("B2_STAGING_BYTES", 1024 * MiB)),
     "n_segments": int(os.environ.get("B2_SEGMENTS", 8)),
-    "max_batch": int(os.environ.get("B2_MAX_BATCH", 1024)),
+    "n_out_segments": int(os.environ.get("B2_OUT_SEGMENTS", 0)) or None,   # default: same as n_segments
+    "max_batch": int(os.environ.get("B2_MAX_BATCH", 2048)),
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
+    "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
 }
 
 
@@ -65,14 +68,16 @@ class DeviceTaskError(RuntimeError):
 
 
 class Batch:
-    """Electrons staged together: one segment pair, one launch, one future."""
+    """Electrons staged together: one ingress segment, one egress segment, one
+    launch, one future."""
 
-    __slots__ = ("engine", "seg", "n", "in_used", "out_used", "table", "future", "loop",
-                 "ticket", "unread", "done", "flushed", "error")
+    __slots__ = ("engine", "seg", "oseg", "n", "in_used", "out_used", "table", "future", "loop",
+                 "ticket", "unread", "done", "flushed", "error", "lease", "zero_copy", "out_freed")
 
-    def __init__(self, engine: "DeviceEngine", seg: int, loop):
+    def __init__(self, engine: "DeviceEngine", seg: int, oseg: int, loop):
         self.engine = engine
         self.seg = seg
+        self.oseg = oseg
         self.n = 0
         self.in_used = 0
         self.out_used = 0
@@ -84,6 +89,9 @@ class Batch:
         self.done = False
         self.flushed = False
         self.error: Optional[BaseException] = None
+        self.lease = None           # ctypes view of the egress segment that result arrays alias
+        self.zero_copy = False
+        self.out_freed = False
 
 
 class Staged:
@@ -95,7 +103,7 @@ class Staged:
                  spec: DeviceElectron):
         self.batch = batch
         self.index = index
-        self.out_off = out_off
+        self.out_off = out_off          # byte offset inside the batch's egress segment
         self.out_bytes = out_bytes
         self.meta = meta
         self.spec = spec
@@ -107,18 +115,21 @@ class DeviceEngine:
         c.update({k: v for k, v in cfg.items() if v is not None})
         self.ordinal = ordinal
         self.n_segments = int(c["n_segments"])
+        self.n_out_segments = int(c["n_out_segments"] or self.n_segments)
         self.max_batch = int(c["max_batch"])
         self.queue_cap = int(c["queue_cap"])
+        self.zero_copy = bool(c["zero_copy"])
         if self.max_batch > self.queue_cap:
             self.max_batch = self.queue_cap
         staging = int(c["staging_bytes"])
-        # each egress segment ends with max_batch status words
         self.seg_bytes = (staging // self.n_segments) & ~(ALIGN - 1)
+        # every egress segment ends with max_batch status words
         self.status_bytes = _round_up(self.max_batch * 4)
-        if self.seg_bytes <= self.status_bytes + ALIGN:
+        self.out_data_bytes = self.seg_bytes - self.status_bytes
+        if self.out_data_bytes <= ALIGN:
             raise ValueError("staging_bytes too small for n_segments/max_batch")
         self.staging_in = self.seg_bytes * self.n_segments
-        self.staging_out = self.seg_bytes * self.n_segments
+        self.staging_out = self.seg_bytes * self.n_out_segments
         self.arena_bytes = max(int(c["arena_bytes"]), self.staging_in + self.staging_out + 64 * MiB)
         self.arena_bytes = _round_up(self.arena_bytes)
         self.egress_base = self.staging_in                      # arena offset of egress mirror
@@ -128,11 +139,14 @@ class DeviceEngine:
         L.call("b2_init", ordinal, self.arena_bytes, self.staging_in, self.staging_out, self.queue_cap)
         self.info = L.DeviceInfo()
         L.call("b2_get_info", ordinal, C.byref(self.info))
-        self._h_in = self._host_view(0, self.staging_in)
-        self._h_out = self._host_view(1, self.staging_out)
+        self._h_in, _ = self._host_view(0, self.staging_in)
+        self._h_out, self._h_out_addr = self._host_view(1, self.staging_out)
         self._tables = [bytearray(64 * self.max_batch) for _ in range(self.n_segments)]
         self._free_segments = list(range(self.n_segments - 1, -1, -1))
-        self._segment_waiters: List[asyncio.Future] = []
+        self._free_out = list(range(self.n_out_segments - 1, -1, -1))
+        self._seg_lock = threading.Lock()          # lease finalizers may run on any thread
+        self._segment_waiters: list = []           # (loop, future)
+        self._leases_out = 0                       # egress segments currently aliased by results
         self._open: Optional[Batch] = None
         self._inflight: List[Batch] = []
         self._registered = 0
@@ -140,19 +154,20 @@ class DeviceEngine:
         self._waitq: "queue.SimpleQueue[Optional[Batch]]" = queue.SimpleQueue()
         self._waiter = threading.Thread(target=self._wait_loop, name=f"b2-wait-{ordinal}", daemon=True)
         self._waiter.start()
-        self.counters = {"electrons": 0, "batches": 0, "bytes_in": 0, "bytes_out": 0}
+        self.counters = {"electrons": 0, "batches": 0, "bytes_in": 0, "bytes_out": 0,
+                         "zero_copy_batches": 0}
         self.closed = False
         self.sync_registry()
 
     # ------------------------------------------------------------- plumbing --
-    def _host_view(self, which: int, nbytes: int) -> np.ndarray:
+    def _host_view(self, which: int, nbytes: int):
         ptr = C.c_void_p()
         size = C.c_uint64()
         L.call("b2_host_buffer", self.ordinal, which, C.byref(ptr), C.byref(size))
         if size.value < nbytes or not ptr.value:
             raise RuntimeError("pinned staging buffer smaller than requested")
         buf = (C.c_uint8 * nbytes).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=np.uint8)
+        return np.frombuffer(buf, dtype=np.uint8), ptr.value
 
     def sync_registry(self) -> None:
         """Push callback-table entries registered since the last call (b2_register)."""
@@ -172,80 +187,96 @@ class DeviceEngine:
 
     # --------------------------------------------------------------- staging --
     def fits(self, enc: EncodedTask) -> bool:
-        need_in = sum(_round_up(p.size) for p in enc.payloads)
-        need_out = _round_up(max(enc.out_bytes, 16))
-        return need_in <= self.seg_bytes and need_out <= self.seg_bytes - self.status_bytes
+        need_in = 0
+        for p in enc.payloads:
+            need_in += _round_up(p.size)
+        return need_in <= self.seg_bytes and _round_up(max(enc.out_bytes, 16)) <= self.out_data_bytes
 
     async def stage(self, enc: EncodedTask) -> Staged:
         """Copy one electron's operands into pinned ingress memory and append
         its task record to the open batch (ssh.py:147-150 + ssh.py:360-361)."""
-        need_in = sum(_round_up(p.size) for p in enc.payloads)
+        need_in = 0
+        for p in enc.payloads:
+            need_in += _round_up(p.size)
         need_out = _round_up(max(enc.out_bytes, 16))
-        if not self.fits(enc):
+        if need_in > self.seg_bytes or need_out > self.out_data_bytes:
             raise ValueError("electron payload larger than one staging segment")
         loop = asyncio.get_running_loop()
         while True:
             b = self._open
-            if b is not None and (b.loop is not loop or b.n >= self.max_batch
-                                  or b.in_used + need_in > self.seg_bytes
-                                  or b.out_used + need_out > self.seg_bytes - self.status_bytes):
+            if b is not None and (b.n >= self.max_batch or b.in_used + need_in > self.seg_bytes
+                                  or b.out_used + need_out > self.out_data_bytes or b.loop is not loop):
                 self.flush()
                 b = None
             if b is None:
-                if not self._free_segments:
+                pair = self._take_segments()
+                if pair is None:
                     self._reap()
-                if not self._free_segments:
+                    pair = self._take_segments()
+                if pair is None:
                     fut = loop.create_future()
-                    self._segment_waiters.append(fut)
+                    self._segment_waiters.append((loop, fut))
                     await fut
                     continue
-                b = Batch(self, self._free_segments.pop(), loop)
+                b = Batch(self, pair[0], pair[1], loop)
                 self._open = b
                 loop.call_soon(self._idle_flush, b)
             break
         return self._append(b, enc)
+
+    def _take_segments(self):
+        with self._seg_lock:
+            if self._free_segments and self._free_out:
+                return self._free_segments.pop(), self._free_out.pop()
+        return None
 
     def _append(self, b: Batch, enc: EncodedTask) -> Staged:
         spec = enc.spec
         if spec.fn_id > self._registered:
             self.sync_registry()
         seg_base = b.seg * self.seg_bytes
-        offs = [0, 0]
+        h_in = self._h_in
         flags = 0
-        if enc.payloads:
-            if spec.kind == L.K_STACK_SUM:
-                # rows are staged back to back at a fixed stride
-                stride = _round_up(enc.payloads[0].size if len(enc.payloads) > 1
-                                   else enc.payloads[0].size // enc.nrows, 16)
-                base = seg_base + b.in_used
-                if len(enc.payloads) == 1:
-                    if stride * enc.nrows != enc.payloads[0].size:
-                        rows = enc.payloads[0].reshape(enc.nrows, -1)
-                        for r in range(enc.nrows):
-                            o = base + r * stride
-                            self._h_in[o:o + rows.shape[1]] = rows[r]
-                    else:
-                        self._h_in[base:base + enc.payloads[0].size] = enc.payloads[0]
-                else:
-                    for r, p in enumerate(enc.payloads):
-                        o = base + r * stride
-                        self._h_in[o:o + p.size] = p
-                b.in_used += _round_up(stride * enc.nrows)
-                offs = [base, stride]
-            else:
-                for i, p in enumerate(enc.payloads):
-                    o = seg_base + b.in_used
-                    self._h_in[o:o + p.size] = p
-                    offs[i] = o
-                    b.in_used += _round_up(p.size)
-        else:
-            offs = [enc.imm[0] & 0xFFFFFFFFFFFFFFFF, enc.imm[1] & 0xFFFFFFFFFFFFFFFF]
+        payloads = enc.payloads
+        if len(payloads) == 1 and not enc.nrows:          # the common case, kept short
+            p = payloads[0]
+            a0 = seg_base + b.in_used
+            h_in[a0:a0 + p.size] = p
+            b.in_used += _round_up(p.size)
+            a1 = 0
+        elif not payloads:
+            a0, a1 = enc.imm[0] & 0xFFFFFFFFFFFFFFFF, enc.imm[1] & 0xFFFFFFFFFFFFFFFF
             flags = L.F_IMM0 | L.F_IMM1
-        out_off = seg_base + b.out_used                      # egress-relative
-        b.out_used += _round_up(max(enc.out_bytes, 16))
+        elif spec.kind == L.K_STACK_SUM:
+            # rows are staged back to back at a fixed, 16 B aligned stride
+            row_bytes = enc.count * 4
+            stride = _round_up(row_bytes, 16)
+            a0, a1 = seg_base + b.in_used, stride
+            if len(payloads) == 1:
+                rows = payloads[0].reshape(enc.nrows, row_bytes)
+                if stride == row_bytes:
+                    h_in[a0:a0 + rows.size] = payloads[0]
+                else:
+                    for r in range(enc.nrows):
+                        h_in[a0 + r * stride:a0 + r * stride + row_bytes] = rows[r]
+            else:
+                for r, p in enumerate(payloads):
+                    h_in[a0 + r * stride:a0 + r * stride + p.size] = p
+            b.in_used += _round_up(stride * enc.nrows)
+        else:
+            offs = []
+            for p in payloads:
+                o = seg_base + b.in_used
+                h_in[o:o + p.size] = p
+                offs.append(o)
+                b.in_used += _round_up(p.size)
+            a0, a1 = offs[0], offs[1]
+        out_off = b.out_used                                 # inside the egress segment
+        b.out_used = out_off + _round_up(max(enc.out_bytes, 16))
         idx = b.n
-        _TASK.pack_into(b.table, idx * 64, spec.fn_id, flags, offs[0], offs[1],
-                        self.egress_base + out_off, enc.count, enc.nrows, 0, 0, 0, 0)
+        _TASK.pack_into(b.table, idx * 64, spec.fn_id, flags, a0, a1,
+                        self.egress_base + b.oseg * self.seg_bytes + out_off, enc.count, enc.nrows,
+                        0, 0, 0, 0)
         b.n = idx + 1
         b.unread += 1
         return Staged(b, idx, out_off, enc.out_bytes, enc.result_meta, spec)
@@ -261,20 +292,25 @@ class DeviceEngine:
             return None
         self._open = None
         if b.n == 0:
-            self._release_segment(b.seg)
+            self._release_in(b.seg)
+            self._release_out(b)
             return None
         b.flushed = True
         dev = self.ordinal
-        seg_base = b.seg * self.seg_bytes
-        status_off = seg_base + self.seg_bytes - self.status_bytes
+        in_base = b.seg * self.seg_bytes
+        out_base = b.oseg * self.seg_bytes
+        status_off = out_base + self.out_data_bytes
+        # results alias pinned memory only while the egress pool is comfortable
+        with self._seg_lock:
+            b.zero_copy = self.zero_copy and len(self._free_out) * 4 >= self.n_out_segments
         try:
             if b.in_used:
-                L.call("b2_h2d", dev, seg_base, seg_base, b.in_used)
+                L.call("b2_h2d", dev, in_base, in_base, b.in_used)
             tab = (C.c_char * (64 * b.n)).from_buffer(b.table)
             L.call("b2_enqueue", dev, C.addressof(tab), b.n, None, 0, None)
             t = C.c_uint64()
             L.call("b2_launch", dev, status_off, C.byref(t))
-            L.call("b2_d2h", dev, self.egress_base + seg_base, seg_base, b.out_used)
+            L.call("b2_d2h", dev, self.egress_base + out_base, out_base, b.out_used)
             L.call("b2_mark", dev, C.byref(t))
             b.ticket = t.value
         except BaseException as err:  # surface on the awaiting coroutines
@@ -324,6 +360,9 @@ class DeviceEngine:
         if b.done:
             return
         b.done = True
+        self._release_in(b.seg)       # the copies out of pinned ingress have finished
+        if b.error is not None or b.unread == 0:
+            self._release_out(b)
         fut = b.future
         if fut is not None and not fut.done():
             if b.error is not None:
@@ -333,38 +372,101 @@ class DeviceEngine:
 
     def status_of(self, s: Staged) -> int:
         b = s.batch
-        off = b.seg * self.seg_bytes + self.seg_bytes - self.status_bytes + 4 * s.index
+        off = b.oseg * self.seg_bytes + self.out_data_bytes + 4 * s.index
         return int(self._h_out[off:off + 4].view(np.uint32)[0])
 
     def result_of(self, s: Staged) -> Any:
-        """Decode one result out of pinned egress memory (ssh.py:451-456)."""
-        return decode(s.meta, self._h_out[s.out_off:s.out_off + max(s.out_bytes, 16)])
+        """Materialise one result (ssh.py:451-456).  Array results alias the
+        batch's pinned egress segment when the pool has room (no copy, no page
+        faults); the segment returns to the pool when the last such array dies.
+        Otherwise they are copied out."""
+        b = s.batch
+        base = b.oseg * self.seg_bytes
+        meta = s.meta
+        if b.zero_copy and meta[0] == "array" and s.out_bytes:
+            lease = b.lease
+            if lease is None:
+                lease = (C.c_uint8 * self.out_data_bytes).from_address(self._h_out_addr + base)
+                fin = weakref.finalize(lease, self._lease_dropped, b.oseg)
+                fin.atexit = False
+                b.lease = lease
+                with self._seg_lock:
+                    self._leases_out += 1
+                self.counters["zero_copy_batches"] += 1
+            arr = np.frombuffer(lease, dtype=meta[1], count=s.out_bytes // 4, offset=s.out_off)
+            return arr.reshape(meta[2], order=meta[3])
+        off = base + s.out_off
+        return decode(meta, self._h_out[off:off + max(s.out_bytes, 16)])
 
     def release(self, s: Staged) -> None:
         """The caller is done with this electron's staging (ssh.py:284-315)."""
         b = s.batch
         b.unread -= 1
         if b.unread == 0 and b.done:
-            self._release_segment(b.seg)
+            self._release_out(b)
 
-    def _release_segment(self, seg: int) -> None:
-        self._free_segments.append(seg)
+    # -------------------------------------------------------- segment pools ---
+    def _release_in(self, seg: int) -> None:
+        with self._seg_lock:
+            self._free_segments.append(seg)
+        self._wake_one()
+
+    def _release_out(self, b: Batch) -> None:
+        """Egress segment back to the pool — unless result arrays alias it, in
+        which case the lease finalizer does it when they are gone."""
+        if b.out_freed:
+            return
+        b.out_freed = True
+        if b.lease is not None:
+            b.lease = None            # drop the batch's own reference; arrays keep theirs
+            return
+        with self._seg_lock:
+            self._free_out.append(b.oseg)
+        self._wake_one()
+
+    def _lease_dropped(self, oseg: int) -> None:
+        if self.closed:
+            return
+        with self._seg_lock:
+            self._free_out.append(oseg)
+            self._leases_out -= 1
+        self._wake_one()
+
+    def _wake_one(self) -> None:
         while self._segment_waiters:
-            fut = self._segment_waiters.pop(0)
-            if not fut.done():
-                fut.set_result(None)
-                break
+            try:
+                loop, fut = self._segment_waiters.pop(0)
+            except IndexError:
+                return
+            if fut.done():
+                continue
+            try:
+                loop.call_soon_threadsafe(_resolve, fut)
+            except RuntimeError:
+                continue
+            return
 
     # ----------------------------------------------------------------- close --
     def close(self) -> None:
         if self.closed:
             return
-        self.closed = True
         self._waitq.put(None)
         try:
             L.call("b2_sync", self.ordinal)
         finally:
+            with self._seg_lock:
+                leaked = self._leases_out
+            self.closed = True
+            if leaked:
+                # live result arrays still point into the pinned egress buffer:
+                # hand it over to them instead of freeing it under their feet
+                L.call("b2_detach_host_buffer", self.ordinal, 1)
             L.call("b2_shutdown", self.ordinal)
+
+
+def _resolve(fut) -> None:
+    if not fut.done():
+        fut.set_result(None)
 
 
 # ---------------------------------------------------------------------------

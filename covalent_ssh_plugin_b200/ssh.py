@@ -31,6 +31,7 @@ import asyncio
 import logging
 import os
 import socket
+import time
 from pathlib import Path
 from typing import Any, Callable, Coroutine, Dict, Optional, Tuple, Union
 
@@ -71,20 +72,54 @@ _EXECUTOR_PLUGIN_DEFAULTS = {
     "create_unique_workdir": False,
 }
 
+def _join(directory: str, name: str) -> str:
+    """os.path.join for a relative ``name`` (the only case on this path), without
+    its per-call overhead: six names are derived per electron."""
+    if not directory:
+        return name
+    return directory + name if directory.endswith("/") else directory + "/" + name
+
+
 _LOCAL_NAMES = ("", "localhost", "127.0.0.1", "::1")
 _GPU_PREFIXES = ("cuda:", "gpu:", "b200:", "cuda", "gpu", "b200")
+
+
+_resolved: Dict[str, int] = {}
 
 
 def resolve_device(hostname: str) -> int:
     """CUDA ordinal named by ``hostname``.  Names that are not GPU names resolve
     the way an unknown DNS name does in the reference: ``socket.gaierror``."""
+    hit = _resolved.get(hostname)
+    if hit is not None:
+        return hit
     h = (hostname or "").strip().lower()
-    if h in _LOCAL_NAMES:
+    if h in _LOCAL_NAMES:         # not cached: follows LOCAL_RANK
         return int(os.environ.get("LOCAL_RANK", os.environ.get("B2_DEFAULT_DEVICE", "0")))
     for p in _GPU_PREFIXES:
         if h.startswith(p) and h[len(p):].isdigit():
-            return int(h[len(p):])
+            _resolved[hostname] = int(h[len(p):])
+            return _resolved[hostname]
     raise socket.gaierror(f"'{hostname}' does not name a GPU of this box (use 'cuda:N')")
+
+
+# key file path -> time.monotonic() of the last successful check.  The reference
+# stats the key file twice per electron (ssh.py:224, 331); a positive answer is
+# reused for one second so that a 10 000-electron fan-out does not issue 20 000
+# stat calls.  A negative answer is never cached.
+_KEY_TTL = 1.0
+_key_seen: Dict[str, float] = {}
+
+
+def _key_file_present(path: str, check) -> bool:
+    now = time.monotonic()
+    if now - _key_seen.get(path, -1e9) < _KEY_TTL:
+        return True
+    if check(path):
+        _key_seen[path] = now
+        return True
+    _key_seen.pop(path, None)
+    return False
 
 
 class DeviceConnection:
@@ -209,11 +244,12 @@ class SSHExecutor(RemoteExecutor):
         later steps find it.  An electron that cannot run on the device is
         recorded with the reason; ``submit_task`` reports it as a failed run.
         """
-        function_file = os.path.join(self.cache_dir, f"function_{operation_id}.pkl")
-        script_file = os.path.join(self.cache_dir, f"exec_{operation_id}.py")
-        remote_function_file = os.path.join(self.remote_cache, f"function_{operation_id}.pkl")
-        remote_script_file = os.path.join(self.remote_cache, f"exec_{operation_id}.py")
-        remote_result_file = os.path.join(self.remote_cache, f"result_{operation_id}.pkl")
+        local, remote = self.cache_dir, self.remote_cache
+        function_file = _join(local, f"function_{operation_id}.pkl")
+        script_file = _join(local, f"exec_{operation_id}.py")
+        remote_function_file = _join(remote, f"function_{operation_id}.pkl")
+        remote_script_file = _join(remote, f"exec_{operation_id}.py")
+        remote_result_file = _join(remote, f"result_{operation_id}.pkl")
 
         try:
             entry = _InFlight(encoded=encode(fn, args, kwargs))
@@ -244,7 +280,7 @@ class SSHExecutor(RemoteExecutor):
     async def _client_connect(self) -> Tuple[bool, Optional[DeviceConnection]]:
         """Open (or reuse) the engine of the GPU named by ``hostname``
         (ssh.py:210-235).  Returns ``(False, None)`` when it cannot be reached."""
-        if not os.path.exists(self.ssh_key_file):
+        if not _key_file_present(self.ssh_key_file, os.path.exists):
             message = f"SSH key file {self.ssh_key_file} does not exist."
             app_log.error(message)
             raise RuntimeError(message)
@@ -276,7 +312,7 @@ class SSHExecutor(RemoteExecutor):
 
     async def _validate_credentials(self) -> bool:
         """The key file must exist (ssh.py:317-335)."""
-        if not Path(self.ssh_key_file).is_file():
+        if not _key_file_present(self.ssh_key_file, os.path.isfile):
             raise RuntimeError(f"SSH key file {self.ssh_key_file} does not exist.")
         return True
 
@@ -390,7 +426,7 @@ class SSHExecutor(RemoteExecutor):
 
         names = self._write_function_files(operation_id, function, args, kwargs, workdir)
         function_file, script_file, remote_function_file, remote_script_file, remote_result_file = names
-        result_file = os.path.join(self.cache_dir, f"result_{operation_id}.pkl")
+        result_file = _join(self.cache_dir, f"result_{operation_id}.pkl")
         released = False
         try:
             await self._upload_task(conn, function_file, remote_function_file, script_file,
@@ -447,10 +483,17 @@ async def _open_engine(ordinal: int, hostname: str) -> DeviceConnection:
     """Engine of one GPU as a connection object.  Translates "no such device /
     device unusable" into ``ConnectionRefusedError`` so the caller's retry and
     fallback policy applies; a missing library propagates untouched."""
+    conn = _connections.get((ordinal, hostname))
+    if conn is not None and not conn.engine.closed:
+        return conn
     try:
         engine = get_engine(ordinal)
     except _b2lib.LibraryMissing:
         raise
     except _b2lib.B2Error as err:
         raise ConnectionRefusedError(f"GPU {ordinal} refused: {err}") from err
-    return DeviceConnection(engine, hostname)
+    conn = _connections[(ordinal, hostname)] = DeviceConnection(engine, hostname)
+    return conn
+
+
+_connections: Dict[tuple, DeviceConnection] = {}

@@ -160,6 +160,10 @@ int b2_get_stats(int dev, b2_stats *out);
 /* ---- memory -------------------------------------------------------------- */
 /* which: 0 = ingress (pinned, host writes / device reads), 1 = egress. */
 int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes);
+/* Ownership of one pinned staging buffer passes to the caller: the library
+ * forgets it and b2_shutdown will not free it.  Used when result arrays that
+ * alias the egress buffer (zero-copy results) outlive the engine. */
+int b2_detach_host_buffer(int dev, int which);
 /* async copies on the device's compute stream; host_off is relative to the
  * pinned staging buffer named by the direction (ssh.py:360-361 / ssh.py:451). */
 int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes);
