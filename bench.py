@@ -210,7 +210,7 @@ def run_cuda_arm(args, dist: Dist):
     n, payload = args.electrons, args.payload
     count = payload // 4
     total = n * payload
-    max_batch = env_int("B2_MAX_BATCH", 2048)
+    max_batch = env_int("B2_MAX_BATCH", 4096)
     # one whole step must fit in flight each way; the egress pool also has to hold
     # every result of a step while the caller still references them (zero-copy)
     per_seg = max_batch * (payload + 256) + (1 << 20)

@@ -47,7 +47,7 @@ DEFAULTS = {
     "staging_bytes": int(os.environ.get("B2_STAGING_BYTES", 1024 * MiB)),
     "n_segments": int(os.environ.get("B2_SEGMENTS", 8)),
     "n_out_segments": int(os.environ.get("B2_OUT_SEGMENTS", 0)) or None,   # default: same as n_segments
-    "max_batch": int(os.environ.get("B2_MAX_BATCH", 2048)),
+    "max_batch": int(os.environ.get("B2_MAX_BATCH", 4096)),
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
     "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
 }
