@@ -201,12 +201,32 @@ def run_reference_arm(args, dist: Dist):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU:
+    the staging memcpy into pinned memory is the host's largest data mover."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # --------------------------------------------------------------- CUDA arm -----
 def run_cuda_arm(args, dist: Dist):
     from covalent_ssh_plugin_b200 import SSHExecutor, _b2lib as L, electrons
     from covalent_ssh_plugin_b200.engine import get_engine, shutdown_all
 
     dev = dist.local_rank
+    if dist.world > 1:
+        bind_to_gpu_numa(dev)
     n, payload = args.electrons, args.payload
     count = payload // 4
     total = n * payload
@@ -289,6 +309,12 @@ def run_cuda_arm(args, dist: Dist):
     dist.barrier()
     ms_step = dist.max(ms_step)
     launches = int((s1.launches_worker - s0.launches_worker) + (s1.launches_pack - s0.launches_pack))
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu capture (bench.py cannot run under ncu)
+        tj = json.loads((REPO / "profiles" / "traffic.json").read_text())["worker_kernel"]
+        traffic = tj["dram_bytes_per_electron"] * n / len(batches)
+    except Exception:
+        pass
     n_launch_per_step = len(batches)
     algo_bytes_per_launch = 2.0 * total / n_launch_per_step
     worker_gbs = (2.0 * total / 1e9) / (ms_step / 1e3)
@@ -375,7 +401,8 @@ def run_cuda_arm(args, dist: Dist):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "b2::worker_kernel (scale_add callback)",
                          "achieved": worker_gbs, "peak": peak, "unit": "GB/s", "frac": worker_gbs / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes_per_launch},
             "kernels": kernels,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
