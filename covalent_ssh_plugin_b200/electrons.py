@@ -25,7 +25,7 @@ import functools
 import inspect
 import threading
 from dataclasses import dataclass
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -249,6 +249,59 @@ def encode(fn: Callable, args, kwargs) -> EncodedTask:
         imm = (pos[0], pos[1] if want == 2 else 0)
         return EncodedTask(spec, (), imm, 1, 0, 8, ("int",))
     raise NotDeviceEligible(f"kind {k} has no encoder")
+
+
+def plan_call(spec: DeviceElectron, operands: Sequence) -> dict:
+    """Shape inference for one call whose operands are known only by metadata —
+    what the lattice compiler needs to lay a whole DAG out in the arena before
+    any electron has run.  ``operands`` holds, per positional argument,
+    ``("array", shape, order)``, ``("int", value)`` or a list of array metas.
+    Returns count / nrows / out_bytes / result_meta, or raises NotDeviceEligible.
+    """
+    k = spec.kind
+
+    def arr(m):
+        if not (isinstance(m, tuple) and m and m[0] == "array"):
+            raise NotDeviceEligible(f"{spec.name}: operand is not a float32 array")
+        if len(m[1]) == 0:
+            raise NotDeviceEligible("0-d arrays behave like numpy scalars on the host")
+        return tuple(m[1]), m[2]
+
+    if k in _ARRAY1:
+        if len(operands) != 1:
+            raise NotDeviceEligible(f"{spec.name} takes one array operand, got {len(operands)}")
+        shape, order = arr(operands[0])
+        n = int(np.prod(shape, dtype=np.int64))
+        if k == K_SUM:
+            return dict(count=n, nrows=0, out_bytes=4, result_meta=("f32",))
+        return dict(count=4 * n if k == K_COPY else n, nrows=0, out_bytes=4 * n,
+                    result_meta=("array", np.float32, shape, order))
+    if k in _ARRAY2:
+        if len(operands) != 2:
+            raise NotDeviceEligible(f"{spec.name} takes two array operands, got {len(operands)}")
+        (s0, o0), (s1, o1) = arr(operands[0]), arr(operands[1])
+        if s0 != s1 or o0 != o1:
+            raise NotDeviceEligible("binary electrons need operands of identical shape and order")
+        n = int(np.prod(s0, dtype=np.int64))
+        return dict(count=n, nrows=0, out_bytes=4 * n, result_meta=("array", np.float32, s0, o0))
+    if k == K_STACK_SUM:
+        if len(operands) != 1 or not isinstance(operands[0], list) or not operands[0]:
+            raise NotDeviceEligible("stack_sum needs a non-empty list of arrays")
+        metas = [arr(m) for m in operands[0]]
+        if any(m != metas[0] or m[1] != "C" for m in metas):
+            raise NotDeviceEligible("stack_sum rows must share one C-ordered shape")
+        n = int(np.prod(metas[0][0], dtype=np.int64))
+        return dict(count=n, nrows=len(metas), out_bytes=4 * n,
+                    result_meta=("array", np.float32, metas[0][0], "C"))
+    if k in _INT2 or k in _INT1:
+        want = 2 if k in _INT2 else 1
+        if len(operands) != want or any(not (isinstance(m, tuple) and m[0] == "int") for m in operands):
+            raise NotDeviceEligible(f"{spec.name} takes {want} integer operand(s)")
+        for m in operands:
+            if type(m[1]) is not int or not INT64_MIN <= m[1] <= INT64_MAX:
+                raise NotDeviceEligible("integer operand outside int64")
+        return dict(count=1, nrows=0, out_bytes=8, result_meta=("int",))
+    raise NotDeviceEligible(f"kind {k} has no planner")
 
 
 def decode(meta: tuple, raw: np.ndarray) -> Any:

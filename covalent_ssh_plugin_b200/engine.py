@@ -109,6 +109,82 @@ class Staged:
         self.spec = spec
 
 
+class Heap:
+    """First-fit allocator over the arena heap [base, base + size), 256 B granules."""
+
+    def __init__(self, base: int, size: int):
+        self.base, self.size = base, size
+        self.free = [(base, size)]            # sorted, coalesced (offset, bytes)
+        self.used: Dict[int, int] = {}
+        self.lock = threading.Lock()
+
+    def alloc(self, nbytes: int) -> int:
+        need = _round_up(max(nbytes, 1))
+        with self.lock:
+            for i, (off, sz) in enumerate(self.free):
+                if sz >= need:
+                    if sz == need:
+                        self.free.pop(i)
+                    else:
+                        self.free[i] = (off + need, sz - need)
+                    self.used[off] = need
+                    return off
+        raise MemoryError(f"arena heap exhausted: need {need} bytes (raise B2_ARENA_BYTES)")
+
+    def release(self, off: int) -> None:
+        with self.lock:
+            sz = self.used.pop(off, None)
+            if sz is None:
+                return
+            import bisect
+
+            i = bisect.bisect_left(self.free, (off, 0))
+            self.free.insert(i, (off, sz))
+            if i + 1 < len(self.free) and self.free[i][0] + self.free[i][1] == self.free[i + 1][0]:
+                self.free[i] = (self.free[i][0], self.free[i][1] + self.free.pop(i + 1)[1])
+            if i > 0 and self.free[i - 1][0] + self.free[i - 1][1] == self.free[i][0]:
+                self.free[i - 1] = (self.free[i - 1][0], self.free[i - 1][1] + self.free.pop(i)[1])
+
+    def bytes_in_use(self) -> int:
+        with self.lock:
+            return sum(self.used.values())
+
+
+class DeviceArray:
+    """A float32 array that lives in a GPU's arena (the device-resident form of
+    an electron result).  ``view(offset_bytes, shape)`` makes non-owning windows,
+    e.g. the rows of a fan-in block."""
+
+    __slots__ = ("engine", "offset", "nbytes", "shape", "order", "owner", "alive", "__weakref__")
+
+    def __init__(self, engine: "DeviceEngine", offset: int, nbytes: int, shape: tuple, order: str = "C",
+                 owner: Optional["DeviceArray"] = None):
+        self.engine, self.offset, self.nbytes = engine, offset, nbytes
+        self.shape, self.order, self.owner = shape, order, owner
+        self.alive = True
+
+    @property
+    def ordinal(self) -> int:
+        return self.engine.ordinal
+
+    def view(self, byte_offset: int, nbytes: int, shape: tuple) -> "DeviceArray":
+        return DeviceArray(self.engine, self.offset + byte_offset, nbytes, shape, "C", owner=self.owner or self)
+
+    def numpy(self) -> np.ndarray:
+        return self.engine.get(self)
+
+    def free(self) -> None:
+        if self.alive and self.owner is None and not self.engine.closed:
+            self.engine.heap.release(self.offset)
+        self.alive = False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceEngine:
     def __init__(self, ordinal: int, **cfg):
         c = dict(DEFAULTS)
@@ -129,7 +205,8 @@ class DeviceEngine:
         if self.out_data_bytes <= ALIGN:
             raise ValueError("staging_bytes too small for n_segments/max_batch")
         self.staging_in = self.seg_bytes * self.n_segments
-        self.staging_out = self.seg_bytes * self.n_out_segments
+        self.ctrl_off = self.seg_bytes * self.n_out_segments       # status words of DAG launches
+        self.staging_out = self.ctrl_off + _round_up(self.queue_cap * 4)
         self.arena_bytes = max(int(c["arena_bytes"]), self.staging_in + self.staging_out + 64 * MiB)
         self.arena_bytes = _round_up(self.arena_bytes)
         self.egress_base = self.staging_in                      # arena offset of egress mirror
@@ -157,7 +234,74 @@ class DeviceEngine:
         self.counters = {"electrons": 0, "batches": 0, "bytes_in": 0, "bytes_out": 0,
                          "zero_copy_batches": 0}
         self.closed = False
+        self.heap = Heap(self.heap_base, self.heap_bytes)
+        self._peer_ids: Dict[int, int] = {}
         self.sync_registry()
+
+    # ------------------------------------------------- device-resident data --
+    def alloc(self, nbytes: int, shape=None, order: str = "C") -> "DeviceArray":
+        """A float32 slot in the arena heap (lattice intermediates, shared operands)."""
+        off = self.heap.alloc(max(int(nbytes), 16))
+        return DeviceArray(self, off, int(nbytes), tuple(shape) if shape is not None else (int(nbytes) // 4,), order)
+
+    def put(self, array: np.ndarray) -> "DeviceArray":
+        """Host ndarray -> arena heap (synchronous; used for lattice inputs and
+        shared operands, not on the per-electron path)."""
+        a = np.asarray(array)
+        if a.dtype != np.float32:
+            raise TypeError("device arrays are float32")
+        order = "F" if (a.flags.f_contiguous and not a.flags.c_contiguous) else "C"
+        flat = np.ascontiguousarray(a.reshape(-1, order="A" if order == "F" else "C"))
+        da = self.alloc(flat.nbytes, a.shape, order)
+        if flat.nbytes:
+            L.call("b2_write", self.ordinal, da.offset, flat.ctypes.data, flat.nbytes)
+        return da
+
+    def get(self, da: "DeviceArray") -> np.ndarray:
+        out = np.empty(da.shape, dtype=np.float32, order=da.order)
+        if da.nbytes:
+            flat = out.reshape(-1, order="A" if da.order == "F" else "C")
+            L.call("b2_read", self.ordinal, da.offset, flat.ctypes.data, da.nbytes)
+        return out
+
+    def peer_arena_id(self, other_ordinal: int) -> int:
+        """Arena id under which this GPU's kernels address ``other_ordinal``'s arena
+        (same-process peers; maps it on first use, b2_peer_enable)."""
+        if other_ordinal == self.ordinal:
+            return 0
+        aid = self._peer_ids.get(other_ordinal)
+        if aid is None:
+            get_engine(other_ordinal)                     # the peer must be up
+            out = C.c_uint32()
+            L.call("b2_peer_enable", self.ordinal, other_ordinal, C.byref(out))
+            aid = self._peer_ids[other_ordinal] = out.value
+        return aid
+
+    def run_dag(self, table: np.ndarray, succ: Optional[np.ndarray] = None) -> np.ndarray:
+        """One worker launch over a whole dependency graph of electrons whose
+        operands already live in the arena: dependents are released on the
+        device through the MPMC queue, no host round trip per edge.  Returns the
+        per-electron status words.  ``table`` has dtype _b2lib.TASK_DTYPE."""
+        n = len(table)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        if n > self.queue_cap:
+            raise ValueError(f"DAG of {n} electrons exceeds queue capacity {self.queue_cap}")
+        self.flush()                       # keep launch order = submission order
+        self.sync_registry()
+        table = np.ascontiguousarray(table)
+        ns = 0 if succ is None else len(succ)
+        sp = None
+        if ns:
+            succ = np.ascontiguousarray(succ, dtype=np.uint32)
+            sp = succ.ctypes.data
+        L.call("b2_enqueue", self.ordinal, table.ctypes.data, n, sp, ns, None)
+        t = C.c_uint64()
+        L.call("b2_launch", self.ordinal, self.ctrl_off, C.byref(t))
+        L.call("b2_wait", self.ordinal, t.value)
+        self.counters["electrons"] += n
+        self.counters["batches"] += 1
+        return self._h_out[self.ctrl_off:self.ctrl_off + 4 * n].view(np.uint32).copy()
 
     # ------------------------------------------------------------- plumbing --
     def _host_view(self, which: int, nbytes: int):

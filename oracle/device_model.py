@@ -70,9 +70,41 @@ def _s64(v: int) -> int:
     return v - (1 << 64) if v >> 63 else v
 
 
-def run_callback(arena: np.ndarray, fn_entry: dict, task: dict) -> int:
-    """Execute one task record against ``arena`` (uint8); returns its status."""
+def run_callback(arena: np.ndarray, fn_entry: dict, task: dict, peers: dict = None) -> int:
+    """Execute one task record against ``arena`` (uint8); returns its status.
+    ``peers`` maps arena ids (b2_task.flags bits 8..19) to other devices' arenas."""
     kind = fn_entry.get("kind", K_NONE)
+    flags = int(task.get("flags", 0))
+    ids = ((flags >> 8) & 15, (flags >> 12) & 15, (flags >> 16) & 15)
+    if any(ids):
+        peers = peers or {}
+        if any(i and i not in peers for i in ids):
+            return TS_BAD_ARG
+        src0 = peers[ids[0]] if ids[0] else arena
+        src1 = peers[ids[1]] if ids[1] else arena
+        dst = peers[ids[2]] if ids[2] else arena
+        # evaluate on a scratch arena laid out like the local one, then write through
+        n_ = int(task["count"])
+        scratch = arena
+        t2 = dict(task)
+        t2["flags"] = flags & 0xFF
+        if ids[0] or ids[1]:
+            esz = 1 if kind == K_COPY else 4
+            span = n_ * esz + (int(task["nrows"]) - 1) * int(task["arg1"]) if kind == K_STACK_SUM else n_ * esz
+            saved = []
+            for which, srcx, off in ((0, src0, int(task["arg0"])), (1, src1, int(task["arg1"]))):
+                if ids[which] and (which == 0 or kind in (K_ADD, K_MUL, K_AXPY)):
+                    saved.append((off, arena[off:off + span].copy()))
+                    arena[off:off + span] = srcx[off:off + span]
+            st = run_callback(arena, fn_entry, t2 if not ids[2] else t2, None)
+            out_bytes = 4 if kind == K_SUM else n_ * (1 if kind == K_COPY else 4)
+            result = arena[int(task["out"]):int(task["out"]) + out_bytes].copy()
+            for off, buf in reversed(saved):
+                arena[off:off + buf.size] = buf
+            dst[int(task["out"]):int(task["out"]) + out_bytes] = result
+            return st
+        st = run_callback(arena, fn_entry, t2, None)
+        return st
     n = int(task["count"])
     out = int(task["out"])
     a0, a1 = int(task["arg0"]), int(task["arg1"])
@@ -129,7 +161,8 @@ def run_callback(arena: np.ndarray, fn_entry: dict, task: dict) -> int:
     return TS_OK
 
 
-def run_tasks(arena: np.ndarray, fn_table: dict, tasks: Sequence[dict], succ: Sequence[int]) -> List[int]:
+def run_tasks(arena: np.ndarray, fn_table: dict, tasks: Sequence[dict], succ: Sequence[int],
+              peers: dict = None) -> List[int]:
     """Batch semantics of the worker: Kahn order over the successor lists."""
     n = len(tasks)
     deps = [int(t["deps"]) for t in tasks]
@@ -139,7 +172,7 @@ def run_tasks(arena: np.ndarray, fn_table: dict, tasks: Sequence[dict], succ: Se
         i = ready.pop(0)
         t = tasks[i]
         entry = fn_table.get(int(t["fn_id"]), {"kind": K_NONE})
-        status[i] = run_callback(arena, entry, t)
+        status[i] = run_callback(arena, entry, t, peers)
         for e in range(int(t["succ_count"])):
             j = int(succ[int(t["succ_begin"]) + e])
             deps[j] -= 1

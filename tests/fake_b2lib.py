@@ -39,6 +39,7 @@ class _Dev:
         self.qcap = qcap
         self.fn = {0: {"kind": M.K_NONE}}
         self.pending, self.pending_succ = [], []
+        self.peers = {}                   # arena id -> peer device ordinal
         self.ticket = 0
         self.stats = dict(launches_pack=0, launches_worker=0, launches_other=1, electrons=0,
                           bytes_packed=0, bytes_h2d=0, bytes_d2h=0)
@@ -138,6 +139,20 @@ class FakeLib:
         d.stats["bytes_d2h"] += n
         return 0
 
+    def b2_write(self, dev, dev_off, src, n):
+        d = self._dev(dev)
+        if dev_off + n > d.arena.size:
+            return self._fail(L.B2_E_ARG, "write range")
+        d.arena[dev_off:dev_off + n] = np.frombuffer((C.c_uint8 * n).from_address(_addr(src)), dtype=np.uint8)
+        return 0
+
+    def b2_read(self, dev, dev_off, dst, n):
+        d = self._dev(dev)
+        if dev_off + n > d.arena.size:
+            return self._fail(L.B2_E_ARG, "read range")
+        np.frombuffer((C.c_uint8 * n).from_address(_addr(dst)), dtype=np.uint8)[:] = d.arena[dev_off:dev_off + n]
+        return 0
+
     # -- callback table + queue ------------------------------------------------------
     def b2_register(self, dev, fn_id, kind, alpha, beta, ialpha, ibeta):
         self._dev(dev).fn[fn_id] = dict(kind=kind, alpha=alpha, beta=beta, ialpha=ialpha, ibeta=ibeta)
@@ -165,12 +180,26 @@ class FakeLib:
         tasks, succ = d.pending, d.pending_succ
         d.pending, d.pending_succ = [], []
         if tasks:
-            status = M.run_tasks(d.arena, d.fn, tasks, succ)
+            peers = {aid: self.devs[o].arena for aid, o in d.peers.items() if o in self.devs}
+            status = M.run_tasks(d.arena, d.fn, tasks, succ, peers)
             d.stats["launches_worker"] += 1
             d.stats["electrons"] += len(tasks)
             if status_off != L.NO_STATUS_COPY:
                 d.h_out[status_off:status_off + 4 * len(tasks)] = np.array(status, dtype=np.uint32).view(np.uint8)
         return self.b2_mark(dev, tref)
+
+    def b2_peer_enable(self, dev, peer, aref):
+        d = self._dev(dev)
+        if peer not in self.devs:
+            return self._fail(L.B2_E_STATE, "peer device is not initialised")
+        for aid, o in d.peers.items():
+            if o == peer:
+                _deref(aref).value = aid
+                return 0
+        aid = len(d.peers) + 1
+        d.peers[aid] = peer
+        _deref(aref).value = aid
+        return 0
 
     def b2_mark(self, dev, tref):
         d = self._dev(dev)

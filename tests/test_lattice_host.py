@@ -1,0 +1,166 @@
+"""The mini lattice driver on CPU (numpy test double of the C ABI): the
+reference's functional-test workflows run unchanged, and graphs of registered
+electrons compile to one device DAG whose results equal plain in-process
+execution of the same Python bodies."""
+
+import numpy as np
+import pytest
+
+from covalent_ssh_plugin_b200 import _b2lib, electrons as E, engine as engine_mod, lattice as ct
+from covalent_ssh_plugin import SSHExecutor
+from tests.fake_b2lib import FakeLib
+
+SMALL = dict(arena_bytes=96 << 20, staging_bytes=16 << 20, n_segments=4, max_batch=64, queue_cap=4096)
+
+
+@pytest.fixture()
+def gpu(tmp_path):
+    engine_mod.shutdown_all()
+    saved = _b2lib._lib
+    _b2lib._lib = FakeLib(n_devices=2)
+    engine_mod.get_engine(0, **SMALL)
+    engine_mod.get_engine(1, **SMALL)
+    key = tmp_path / "k"
+    key.touch()
+    mk = lambda host: SSHExecutor(username="u", hostname=host, ssh_key_file=str(key), cache_dir=str(tmp_path))  # noqa: E731
+    yield mk
+    engine_mod.shutdown_all()
+    _b2lib._lib = saved
+
+
+def test_basic_workflow_like_the_reference():
+    """basic_workflow_test.py:7-29 with local electrons (no server needed)."""
+    @ct.electron
+    def join_words(a, b):
+        return ", ".join([a, b])
+
+    @ct.electron
+    def excitement(a):
+        return f"{a}!"
+
+    @ct.lattice
+    def basic_workflow(a, b):
+        return excitement(join_words(a, b))
+
+    result = ct.get_result(ct.dispatch(basic_workflow)("Hello", "World"), wait=True)
+    assert str(result.status) == str(ct.status.COMPLETED) and result.result == "Hello, World!"
+
+
+def test_failing_electron_fails_the_lattice(gpu):
+    """basic_workflow_test.py:32-49: an electron that raises -> FAILED."""
+    @ct.electron(executor=gpu("cuda:0"))
+    def join_words(a, b):
+        raise Exception(f"{', '.join([a, b])} -- but something went wrong!")
+
+    @ct.lattice
+    def wf(a, b):
+        return join_words(a, b)
+
+    result = ct.get_result(ct.dispatch(wf)("Hello", "World"))
+    assert result.status == ct.status.FAILED and isinstance(result.error, RuntimeError)
+
+
+def test_int_chain_goes_through_the_device(gpu):
+    """BASELINE config 1: add(3,4) then add(prev,5)."""
+    add = ct.electron(E.add_int, executor=gpu("cuda:0"))
+
+    @ct.lattice
+    def wf(a, b):
+        return add(add(a, b), 5)
+
+    r = ct.get_result(ct.dispatch(wf)(3, 4))
+    assert r.status == ct.status.COMPLETED and r.result == 12 and type(r.result) is int
+    assert r.stats["device_electrons"] == 2 and r.stats["host_electrons"] == 0
+
+
+def _diamond(ex, n_fan, n, seed=0):
+    root = ct.electron(E.plus_one, executor=ex(0))
+    scale = [ct.electron(E.scale_add if i % 2 else E.plus_one, executor=ex(i)) for i in range(n_fan)]
+    mul = [ct.electron(E.vec_mul, executor=ex(i)) for i in range(n_fan)]
+    reduce_ = ct.electron(E.stack_sum, executor=ex(0))
+    rng = np.random.default_rng(seed)
+    x0 = rng.random(n, dtype=np.float32)
+    ws = [rng.random(n, dtype=np.float32) for _ in range(n_fan)]
+
+    @ct.lattice
+    def wf(x, weights):
+        r = root(x)
+        return reduce_([mul[i](scale[i](r), weights[i]) for i in range(n_fan)])
+
+    def host(x, weights):
+        r = E.plus_one(x)
+        return E.stack_sum([E.vec_mul((E.scale_add if i % 2 else E.plus_one)(r), weights[i]) for i in range(n_fan)])
+
+    return wf, host, x0, ws
+
+
+def test_diamond_compiles_to_one_device_dag(gpu):
+    ex0 = gpu("cuda:0")
+    wf, host, x0, ws = _diamond(lambda i: ex0, 24, 5000)
+    r = ct.get_result(ct.dispatch(wf)(x0, ws))
+    assert r.status == ct.status.COMPLETED, r.error
+    assert np.array_equal(r.result, host(x0, ws))                     # bit-exact vs the Python bodies
+    assert r.stats["device_batches"] == 1 and r.stats["device_electrons"] == 2 * 24 + 2
+    assert r.stats["host_electrons"] == 0 and "demoted" not in r.stats
+    assert engine_mod.existing_engine(0).heap.bytes_in_use() == 0     # every intermediate was freed
+
+
+def test_wide_fan_in_is_split_by_column(gpu, monkeypatch):
+    monkeypatch.setattr(ct, "SPLIT_MIN_BYTES", 1 << 16)
+    monkeypatch.setattr(ct, "SLICE_ELEMS", 1024)
+    ex0 = gpu("cuda:0")
+    wf, host, x0, ws = _diamond(lambda i: ex0, 16, 5000, seed=3)
+    r = ct.get_result(ct.dispatch(wf)(x0, ws))
+    assert r.status == ct.status.COMPLETED, r.error
+    assert np.array_equal(r.result, host(x0, ws))
+    assert engine_mod.existing_engine(0).counters["electrons"] > 2 * 16 + 2   # gate + slices + join
+
+
+def test_diamond_across_two_gpus_runs_level_by_level(gpu):
+    exs = [gpu("cuda:0"), gpu("cuda:1")]
+    wf, host, x0, ws = _diamond(lambda i: exs[i % 2], 10, 3000, seed=5)
+    r = ct.get_result(ct.dispatch(wf)(x0, ws))
+    assert r.status == ct.status.COMPLETED, r.error
+    assert np.array_equal(r.result, host(x0, ws))
+    # root (level 0), scale (1), mul (2), row copies from the other GPU (3), reduce (4)
+    assert "demoted" not in r.stats and r.stats["device_batches"] >= 5
+
+
+def test_mixed_host_and_device_electrons(gpu):
+    ex0 = gpu("cuda:0")
+    dev_scale = ct.electron(E.scale_add, executor=ex0)
+    dev_sum = ct.electron(E.vec_sum, executor=ex0)
+
+    @ct.electron
+    def make(n):
+        return np.arange(n, dtype=np.float32)
+
+    @ct.electron
+    def describe(total, arr):
+        return f"{float(total):.1f}/{arr.shape[0]}"
+
+    @ct.lattice
+    def wf(n):
+        a = dev_scale(make(n))
+        return describe(dev_sum(a), a)
+
+    r = ct.get_result(ct.dispatch(wf)(100))
+    assert r.status == ct.status.COMPLETED, r.error
+    assert r.result == f"{float((2 * np.arange(100, dtype=np.float32) + 1).sum()):.1f}/100"
+    assert r.stats["host_electrons"] == 2 and r.stats["device_electrons"] == 2
+
+
+def test_overflow_in_a_dag_is_demoted_to_the_executor_decision(gpu):
+    big = (1 << 63) - 1
+    ex = gpu("cuda:0")
+    add = ct.electron(E.add_int, executor=ex)
+
+    @ct.lattice
+    def wf(a):
+        return add(a, 1)
+
+    r = ct.get_result(ct.dispatch(wf)(big))
+    assert r.status == ct.status.FAILED and isinstance(r.error, RuntimeError)
+    ex.run_local_on_ssh_fail = True
+    r = ct.get_result(ct.dispatch(wf)(big))
+    assert r.status == ct.status.COMPLETED and r.result == big + 1
