@@ -43,7 +43,7 @@ def gpu_count(built_library):
     return _cuda_device_count()
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture(scope="module")
 def raw_device(gpu_count):
     """A bare b2_init'ed device 0 for kernel-level tests (no Python engine)."""
     if gpu_count < 1:
