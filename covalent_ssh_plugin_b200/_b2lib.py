@@ -118,6 +118,7 @@ _SIGNATURES = {
     "b2_get_info": ([C.c_int, C.POINTER(DeviceInfo)], True),
     "b2_get_stats": ([C.c_int, C.POINTER(Stats)], True),
     "b2_host_buffer": ([C.c_int, C.c_int, C.POINTER(C.c_void_p), _u64p], True),
+    "b2_arena_base": ([C.c_int, C.c_uint32, C.POINTER(C.c_void_p), _u64p], True),
     "b2_detach_host_buffer": ([C.c_int, C.c_int], True),
     "b2_h2d": ([C.c_int, C.c_uint64, C.c_uint64, C.c_uint64], True),
     "b2_d2h": ([C.c_int, C.c_uint64, C.c_uint64, C.c_uint64], True),

@@ -175,6 +175,14 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   const size_t base_off = (table_bytes + 255) & ~size_t(255);
   const size_t total = base_off + ((size_t)n + 1) * sizeof(uint32_t);
   Staging &s = D->span_ring[D->span_slot];
+  if (total > s.cap) {
+    // grow every slot of the ring in the same call: later calls of this size find
+    // all of them ready and never allocate (allocation synchronises the device)
+    for (auto &other : D->span_ring) {
+      int rc_ = staging_reserve(other, total + total / 4);
+      if (rc_) return rc_;
+    }
+  }
   int rc = staging_reserve(s, total);
   if (rc) return rc;
   D->span_slot = (D->span_slot + 1) % kRing;
@@ -208,7 +216,12 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   base[n] = (uint32_t)chunks;
   if (chunks == 0) return B2_OK;
 
-  CU(cudaMemcpyAsync(s.d, s.h, total, cudaMemcpyHostToDevice, D->stream));
+  // like the task tables, the span table uploads on its own stream so that it
+  // overlaps whatever the compute stream is still running
+  if (!s.up) CU(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
+  CU(cudaMemcpyAsync(s.d, s.h, total, cudaMemcpyHostToDevice, D->upload));
+  CU(cudaEventRecord(s.up, D->upload));
+  CU(cudaStreamWaitEvent(D->stream, s.up, 0));
 
   const uint32_t cps = uniform ? (uint32_t)((b0 + kChunkBytes - 1) / kChunkBytes) : 0u;
   const int warps_per_cta = kMoveThreads / kWarp;
@@ -440,6 +453,15 @@ int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes) {
   } else {
     return fail(B2_E_ARG, "which must be 0 (ingress) or 1 (egress)");
   }
+  return B2_OK;
+}
+
+int b2_arena_base(int dev, uint32_t arena_id, void **ptr, uint64_t *bytes) {
+  if (!ptr || !bytes) return fail(B2_E_ARG, "ptr/bytes is NULL");
+  DEV_OR_FAIL(D, dev);
+  if (arena_id >= (uint32_t)D->n_arenas) return fail(B2_E_ARG, "unknown arena id %u", arena_id);
+  *ptr = D->arena[arena_id];
+  *bytes = D->arena_bytes[arena_id];
   return B2_OK;
 }
 

@@ -113,6 +113,57 @@ def exchange_peer_arenas(ordinal: int, arena_bytes: int) -> Dict[int, int]:
     return arena_ids
 
 
+class _ArenaWindow:
+    """Exposes a byte range of an arena through __cuda_array_interface__ so that
+    torch can wrap it without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2}
+
+
+def broadcast_shared(engine, array, root: int = 0):
+    """A shared dependency — the same operand for electrons on every rank — is
+    uploaded once on ``root`` and broadcast into every rank's arena (the only
+    collective on this path).  Returns a DeviceArray that can be
+    passed as an electron argument.  ``array`` is only read on ``root``.
+
+    NCCL backend: ncclBroadcast directly between arenas (device to device over
+    NVLink).  Other backends (gloo in the CPU tests): broadcast of the host bytes,
+    then a local upload.
+    """
+    import torch
+    import torch.distributed as dist
+
+    single = not dist.is_initialized() or dist.get_world_size() == 1
+    me = 0 if single else dist.get_rank()
+    if me == root:
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        meta = [tuple(a.shape), int(a.nbytes)]
+    else:
+        a, meta = None, [None, None]
+    if not single:
+        dist.broadcast_object_list(meta, src=root)
+    shape, nbytes = tuple(meta[0]), int(meta[1])
+    if single:
+        return engine.put(a)
+    if dist.get_backend() == "nccl":
+        from . import _b2lib as L
+
+        da = engine.put(a) if me == root else engine.alloc(nbytes, shape)
+        ptr, size = C.c_void_p(), C.c_uint64()
+        L.call("b2_arena_base", engine.ordinal, 0, C.byref(ptr), C.byref(size))
+        L.call("b2_sync", engine.ordinal)
+        window = _ArenaWindow(ptr.value + da.offset, nbytes)
+        t = torch.as_tensor(window, device=torch.device("cuda", engine.ordinal))
+        dist.broadcast(t, src=root)
+        torch.cuda.synchronize(engine.ordinal)
+        return da
+    buf = torch.from_numpy(a.reshape(-1).view(np.uint8).copy()) if me == root else torch.empty(nbytes, dtype=torch.uint8)
+    dist.broadcast(buf, src=root)
+    return engine.put(buf.numpy().view(np.float32).reshape(shape))
+
+
 def spans_array(rows: Sequence[tuple]) -> np.ndarray:
     """(src_off, dst_off, bytes) rows as the uint64 array the C ABI takes."""
     return np.ascontiguousarray(np.array(rows, dtype=np.uint64).reshape(-1, 3))

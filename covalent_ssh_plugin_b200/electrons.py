@@ -170,8 +170,23 @@ def _positional(fn: Callable, args, kwargs) -> tuple:
     return tuple(bound.args)
 
 
-def _as_operand(x: Any) -> Tuple[np.ndarray, tuple, str]:
-    """(flat uint8 view of the raw buffer, shape, order) of a float32 ndarray."""
+class DeviceRef:
+    """An operand that already lives in a GPU arena (engine.DeviceArray): nothing is
+    staged for it, the task record points at it."""
+
+    __slots__ = ("ordinal", "offset", "size")
+
+    def __init__(self, ordinal: int, offset: int, size: int):
+        self.ordinal, self.offset, self.size = ordinal, offset, size
+
+
+def _as_operand(x: Any) -> Tuple[Any, tuple, str]:
+    """(flat uint8 view of the raw buffer — or a DeviceRef —, shape, order) of a
+    float32 ndarray / device-resident array."""
+    if getattr(x, "__b200_device_array__", False):
+        if not x.alive:
+            raise NotDeviceEligible("device array has been freed")
+        return DeviceRef(x.ordinal, x.offset, x.nbytes), tuple(x.shape), x.order
     if type(x) is not np.ndarray or x.dtype != np.float32:
         raise NotDeviceEligible("array operands must be float32 numpy.ndarray")
     if x.ndim == 0:
@@ -230,6 +245,8 @@ def encode(fn: Callable, args, kwargs) -> EncodedTask:
             if not isinstance(seq, (list, tuple)) or not seq:
                 raise NotDeviceEligible("stack_sum needs a non-empty list of arrays")
             ops = [_as_operand(a) for a in seq]
+            if any(type(o[0]) is DeviceRef for o in ops):
+                raise NotDeviceEligible("device-resident rows go through the lattice compiler, not run()")
             if any(o[1] != ops[0][1] or o[2] != "C" for o in ops):
                 raise NotDeviceEligible("stack_sum rows must share one C-ordered shape")
             raws = tuple(o[0] for o in ops)

@@ -34,7 +34,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import _b2lib as L
-from .electrons import DeviceElectron, EncodedTask, decode, registry_size, registry_snapshot
+from .electrons import DeviceElectron, DeviceRef, EncodedTask, decode, registry_size, registry_snapshot
 
 _TASK = struct.Struct("<IIQQQQIIIIQ")
 assert _TASK.size == 64
@@ -156,6 +156,7 @@ class DeviceArray:
     e.g. the rows of a fan-in block."""
 
     __slots__ = ("engine", "offset", "nbytes", "shape", "order", "owner", "alive", "__weakref__")
+    __b200_device_array__ = True
 
     def __init__(self, engine: "DeviceEngine", offset: int, nbytes: int, shape: tuple, order: str = "C",
                  owner: Optional["DeviceArray"] = None):
@@ -333,7 +334,8 @@ class DeviceEngine:
     def fits(self, enc: EncodedTask) -> bool:
         need_in = 0
         for p in enc.payloads:
-            need_in += _round_up(p.size)
+            if type(p) is not DeviceRef:
+                need_in += _round_up(p.size)
         return need_in <= self.seg_bytes and _round_up(max(enc.out_bytes, 16)) <= self.out_data_bytes
 
     async def stage(self, enc: EncodedTask) -> Staged:
@@ -341,7 +343,8 @@ class DeviceEngine:
         its task record to the open batch (ssh.py:147-150 + ssh.py:360-361)."""
         need_in = 0
         for p in enc.payloads:
-            need_in += _round_up(p.size)
+            if type(p) is not DeviceRef:
+                need_in += _round_up(p.size)
         need_out = _round_up(max(enc.out_bytes, 16))
         if need_in > self.seg_bytes or need_out > self.out_data_bytes:
             raise ValueError("electron payload larger than one staging segment")
@@ -382,8 +385,8 @@ class DeviceEngine:
         h_in = self._h_in
         flags = 0
         payloads = enc.payloads
-        if len(payloads) == 1 and not enc.nrows:          # the common case, kept short
-            p = payloads[0]
+        if len(payloads) == 1 and not enc.nrows and type(payloads[0]) is not DeviceRef:
+            p = payloads[0]                               # the common case, kept short
             a0 = seg_base + b.in_used
             h_in[a0:a0 + p.size] = p
             b.in_used += _round_up(p.size)
@@ -409,12 +412,17 @@ class DeviceEngine:
             b.in_used += _round_up(stride * enc.nrows)
         else:
             offs = []
-            for p in payloads:
+            for i, p in enumerate(payloads):
+                if type(p) is DeviceRef:                  # already in an arena: point at it
+                    offs.append(p.offset)
+                    if p.ordinal != self.ordinal:
+                        flags |= self.peer_arena_id(p.ordinal) << (L.F_ARENA0_SHIFT, L.F_ARENA1_SHIFT)[i]
+                    continue
                 o = seg_base + b.in_used
                 h_in[o:o + p.size] = p
                 offs.append(o)
                 b.in_used += _round_up(p.size)
-            a0, a1 = offs[0], offs[1]
+            a0, a1 = offs[0], (offs[1] if len(offs) > 1 else 0)
         out_off = b.out_used                                 # inside the egress segment
         b.out_used = out_off + _round_up(max(enc.out_bytes, 16))
         idx = b.n

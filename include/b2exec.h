@@ -160,6 +160,10 @@ int b2_get_stats(int dev, b2_stats *out);
 /* ---- memory -------------------------------------------------------------- */
 /* which: 0 = ingress (pinned, host writes / device reads), 1 = egress. */
 int b2_host_buffer(int dev, int which, void **ptr, uint64_t *bytes);
+/* Raw device pointer and size of an arena (0 = local, else a mapped peer) so that
+ * plumbing outside this library — an NCCL broadcast of a shared operand — can
+ * address arena memory.  The memory stays owned by the library. */
+int b2_arena_base(int dev, uint32_t arena_id, void **ptr, uint64_t *bytes);
 /* Ownership of one pinned staging buffer passes to the caller: the library
  * forgets it and b2_shutdown will not free it.  Used when result arrays that
  * alias the egress buffer (zero-copy results) outlive the engine. */

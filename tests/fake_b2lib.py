@@ -119,6 +119,12 @@ class FakeLib:
         _deref(sref).value = buf.size
         return 0
 
+    def b2_arena_base(self, dev, arena_id, pref, sref):
+        d = self._dev(dev)
+        _deref(pref).value = d.arena.ctypes.data
+        _deref(sref).value = d.arena.size
+        return 0
+
     def b2_detach_host_buffer(self, dev, which):
         self.detached = getattr(self, "detached", []) + [(dev, which, self._dev(dev).h_out)]
         return 0

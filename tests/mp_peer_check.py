@@ -68,8 +68,30 @@ def main():
           f"{gbs:.1f} GB/s per direction (kernel remote stores over NVLink), slowest rank {worst:.3f} ms", flush=True)
     dist.barrier()
     L.call("b2_shutdown", dev)
+
+    # shared dependency: uploaded on rank 0, ncclBroadcast arena -> arena, then used as an
+    # ordinary electron operand on every rank
+    import asyncio
+    import tempfile
+
+    from covalent_ssh_plugin_b200 import SSHExecutor, electrons
+    from covalent_ssh_plugin_b200.engine import get_engine, shutdown_all
+
+    eng = get_engine(dev, arena_bytes=2 << 30, staging_bytes=256 << 20, n_segments=4, max_batch=256)
+    shared_host = np.random.default_rng(99).standard_normal(1 << 20, dtype=np.float32)      # 4 MiB
+    da = D.broadcast_shared(eng, shared_host if rank == 0 else None, root=0)
+    tmp = tempfile.mkdtemp()
+    key = Path(tmp) / "k"
+    key.touch()
+    ex = SSHExecutor(username="u", hostname=f"cuda:{dev}", ssh_key_file=str(key), cache_dir=tmp)
+    x = np.random.default_rng([5, rank]).standard_normal(1 << 20, dtype=np.float32)
+    y = asyncio.run(ex.run(electrons.vec_add, [x, da], {}, {"dispatch_id": "shared", "node_id": rank}))
+    ok2 = np.array_equal(y, x + shared_host)
+    print(f"rank {rank}: shared operand via ncclBroadcast + vec_add on cuda:{dev}: {'OK' if ok2 else 'MISMATCH'}", flush=True)
+    dist.barrier()
+    shutdown_all()
     dist.destroy_process_group()
-    if not ok:
+    if not (ok and ok2):
         sys.exit(1)
 
 

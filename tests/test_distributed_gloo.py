@@ -41,7 +41,19 @@ def _rank_main(rank, world, port, q):
         slow = D.max_over_ranks(1.0 + rank)                    # every rank must see the slowest
         blobs = D.all_gather_bytes(bytes([rank]) * 72)         # same size as an IPC record
         mine = list(D.shard(11, rank, world))
-        q.put((rank, slow, [b[0] for b in blobs], [len(b) for b in blobs], mine))
+        # shared dependency: rank 0's array lands in every rank's arena (host path under gloo)
+        import numpy as np
+
+        from covalent_ssh_plugin_b200 import _b2lib, engine as engine_mod
+        from tests.fake_b2lib import FakeLib
+
+        _b2lib._lib = FakeLib(n_devices=2)
+        eng = engine_mod.get_engine(rank, arena_bytes=48 << 20, staging_bytes=8 << 20, n_segments=2,
+                                    max_batch=16, queue_cap=64)
+        src = np.arange(600, dtype=np.float32).reshape(20, 30) if rank == 0 else None
+        da = D.broadcast_shared(eng, src, root=0)
+        shared_ok = bool(np.array_equal(da.numpy(), np.arange(600, dtype=np.float32).reshape(20, 30)))
+        q.put((rank, slow, [b[0] for b in blobs], [len(b) for b in blobs], mine, shared_ok))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -64,3 +76,4 @@ def test_two_gloo_ranks():
     assert [g[1] for g in got] == [2.0, 2.0]
     assert all(g[2] == [0, 1] and g[3] == [72, 72] for g in got)
     assert sorted(got[0][4] + got[1][4]) == list(range(11))
+    assert all(g[5] for g in got)

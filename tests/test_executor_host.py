@@ -457,3 +457,35 @@ def test_zero_copy_can_be_disabled(fake_lib, tmp_path):
     x = np.arange(4096, dtype=np.float32)
     r = asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "c", "node_id": 0}))
     assert r.flags.owndata and sorted(eng._free_out) == [0, 1, 2, 3]
+
+
+def test_device_resident_operand_through_run(fake_lib, tmp_path):
+    """A shared dependency uploaded once (engine.put / broadcast_shared) is an
+    ordinary electron argument afterwards: nothing is staged for it."""
+    eng = engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path)
+    shared = np.random.default_rng(1).standard_normal(3000, dtype=np.float32)
+    da = eng.put(shared)
+    xs = [np.random.default_rng(10 + i).standard_normal(3000, dtype=np.float32) for i in range(20)]
+    before = eng.counters["bytes_in"]
+
+    async def go():
+        return await asyncio.gather(*[
+            ex.run(electrons.vec_add, [xs[i], da], {}, {"dispatch_id": "sh", "node_id": i}) for i in range(20)])
+
+    out = asyncio.run(go())
+    for i in range(20):
+        assert np.array_equal(out[i], xs[i] + shared)
+    assert eng.counters["bytes_in"] - before == 20 * 12032          # only the 20 private operands were staged
+    da.free()
+    with pytest.raises(RuntimeError, match="freed"):
+        asyncio.run(ex.run(electrons.vec_add, [xs[0], da], {}, META))
+
+
+def test_broadcast_shared_single_process(fake_lib):
+    from covalent_ssh_plugin_b200 import distributed as D
+
+    eng = engine_mod.get_engine(0, **SMALL)
+    x = np.arange(12, dtype=np.float32).reshape(3, 4)
+    da = D.broadcast_shared(eng, x)
+    assert da.shape == (3, 4) and np.array_equal(da.numpy(), x)

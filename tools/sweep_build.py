@@ -9,6 +9,6 @@ sys.path.insert(0, str(REPO))
 from covalent_ssh_plugin_b200.build import build_variant  # noqa: E402
 
 out = REPO / "build" / "variants"
-for ctas, vec in itertools.product((4, 6, 8), (4, 8)):
+for ctas, vec in [(4, 4), (5, 4), (6, 4), (5, 2), (6, 2), (7, 2)]:
     p = build_variant(out / f"w{ctas}_v{vec}.so", {"B2_WORKER_MIN_CTAS": ctas, "B2_WORKER_VEC": vec})
     print(p)
