@@ -35,7 +35,7 @@ import time
 from pathlib import Path
 from typing import Any, Callable, Coroutine, Dict, Optional, Tuple, Union
 
-from . import _b2lib
+from . import _b2lib, hostpool
 from .electrons import NotDeviceEligible, encode
 from .engine import DeviceEngine, Staged, get_engine
 
@@ -156,12 +156,14 @@ class _InFlight:
     """Book-keeping for one electron between the helper calls of ``run``; keyed
     by the same artefact names the reference uses as file names."""
 
-    __slots__ = ("encoded", "staged", "reason")
+    __slots__ = ("encoded", "staged", "reason", "host_call", "host_result")
 
     def __init__(self, encoded=None, reason: str = ""):
         self.encoded = encoded
         self.staged: Optional[Staged] = None
         self.reason = reason
+        self.host_call = None        # (fn, args, kwargs, workdir) when the opt-in host pool takes it
+        self.host_result = None      # (result, exception) from the host pool
 
 
 # name (any of the five artefact names) -> _InFlight; process-wide like a cache dir
@@ -255,6 +257,8 @@ class SSHExecutor(RemoteExecutor):
             entry = _InFlight(encoded=encode(fn, args, kwargs))
         except NotDeviceEligible as why:
             entry = _InFlight(reason=str(why))
+            if hostpool.enabled(get_config):      # opt-in: arbitrary Python runs in warm host workers
+                entry.host_call = (fn, args, kwargs, current_remote_workdir)
         _inflight[function_file] = entry
         _inflight[remote_script_file] = entry
         _inflight[remote_result_file] = entry
@@ -344,6 +348,11 @@ class SSHExecutor(RemoteExecutor):
         entry = _inflight.get(remote_script_file)
         if entry is None:
             return CompletedElectron(127, f"{remote_script_file}: no such electron")
+        if entry.host_call is not None:
+            code, stderr, result, exception = await hostpool.call(*entry.host_call)
+            if code == 0:
+                entry.host_result = (result, exception)
+            return CompletedElectron(code, stderr)
         if entry.staged is None:
             return CompletedElectron(126, entry.reason or "electron was not uploaded")
         staged = entry.staged
@@ -363,6 +372,8 @@ class SSHExecutor(RemoteExecutor):
     async def get_status(self, conn: DeviceConnection, remote_result_file: str) -> bool:
         """True when the electron's result is readable (ssh.py:388-406)."""
         entry = _inflight.get(remote_result_file)
+        if entry is not None and entry.host_result is not None:
+            return True
         return bool(entry and entry.staged is not None and entry.staged.batch.done
                     and entry.staged.batch.error is None)
 
@@ -381,6 +392,8 @@ class SSHExecutor(RemoteExecutor):
         """``(result, exception)`` of the electron (ssh.py:434-458).  Device
         callbacks cannot raise, so ``exception`` is always ``None`` here."""
         entry = _inflight[remote_result_file]
+        if entry.host_result is not None:
+            return entry.host_result
         return conn.engine.result_of(entry.staged), None
 
     async def cleanup(

@@ -489,3 +489,51 @@ def test_broadcast_shared_single_process(fake_lib):
     x = np.arange(12, dtype=np.float32).reshape(3, 4)
     da = D.broadcast_shared(eng, x)
     assert da.shape == (3, 4) and np.array_equal(da.numpy(), x)
+
+
+# ------------------------------------------------------------------ host pool ---
+def _where_am_i():
+    import os
+    return os.getcwd()
+
+
+def _die():
+    import os
+    os._exit(7)
+
+
+def test_host_pool_is_opt_in_and_mirrors_exec_py(fake_lib, tmp_path):
+    """Unregistered electrons: refused by default; with the pool switched on they run
+    in warm worker processes with exec.py's semantics (workdir, in-band exception,
+    crash = non-zero exit).  Device electrons never go there."""
+    import cloudpickle
+
+    from covalent_ssh_plugin_b200 import hostpool
+    import tests.test_executor_host as me
+
+    cloudpickle.register_pickle_by_value(me)
+    cloudpickle.register_pickle_by_value(cases)
+    engine_mod.get_engine(0, **SMALL)
+    wd = tmp_path / "wd"
+    ex = make_executor(tmp_path, remote_workdir=str(wd), create_unique_workdir=True)
+    with pytest.raises(RuntimeError, match="not a registered device electron"):
+        asyncio.run(ex.run(cases.plain_python, ["a", "b"], {}, {"dispatch_id": "hp", "node_id": 0}))
+    with patch.dict(os.environ, {"B2_HOST_POOL": "1", "B2_HOST_POOL_WORKERS": "2"}):
+        try:
+            before = hostpool.stats["submitted"]
+            assert asyncio.run(ex.run(cases.plain_python, ["a", "b"], {}, {"dispatch_id": "hp", "node_id": 1})) == "a, b"
+            assert asyncio.run(ex.run(_where_am_i, [], {}, {"dispatch_id": "hp", "node_id": 2})) == str(wd / "hp" / "node_2")
+            with pytest.raises(ValueError) as ei:
+                asyncio.run(ex.run(cases.raise_value_error, ["boom", 7], {}, {"dispatch_id": "hp", "node_id": 3}))
+            assert ei.value.args == ("boom", 7)
+            with pytest.raises(RuntimeError, match="worker process died"):
+                asyncio.run(ex.run(_die, [], {}, {"dispatch_id": "hp", "node_id": 4}))
+            # the pool recovers, and device electrons still run on the device
+            assert asyncio.run(ex.run(cases.plain_python, ["c", "d"], {}, {"dispatch_id": "hp", "node_id": 5})) == "c, d"
+            n_dev = engine_mod.existing_engine(0).counters["electrons"]
+            assert asyncio.run(ex.run(electrons.add_int, [2, 3], {}, {"dispatch_id": "hp", "node_id": 6})) == 5
+            assert engine_mod.existing_engine(0).counters["electrons"] == n_dev + 1
+            assert hostpool.stats["submitted"] - before == 5
+        finally:
+            hostpool.shutdown()
+    assert not __import__("covalent_ssh_plugin_b200.ssh", fromlist=["_inflight"])._inflight
