@@ -125,30 +125,35 @@ class Dist:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.torch = None
-        if self.world > 1:
+        if self.world > 1 or os.environ.get("B2_BENCH_FORCE_TORCH") == "1":
             import torch
             import torch.distributed as dist
 
             self.torch, self.dist = torch, dist
             torch.cuda.set_device(self.local_rank)
+            if self.world == 1:          # experiment switch: same plumbing as a multi-rank run
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29499")
+                os.environ.setdefault("RANK", "0")
+                os.environ.setdefault("WORLD_SIZE", "1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         if n_gpus != self.world:
             if self.world == 1 and n_gpus > 1:
                 raise SystemExit(f"--gpus {n_gpus} needs torchrun --nproc-per-node {n_gpus}")
 
     def barrier(self):
-        if self.world > 1:
+        if self.torch is not None:
             self.dist.barrier()
 
     def max(self, v: float) -> float:
-        if self.world == 1:
+        if self.torch is None:
             return v
         t = self.torch.tensor([v], dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
     def close(self):
-        if self.world > 1:
+        if self.torch is not None:
             self.dist.destroy_process_group()
 
 
@@ -225,7 +230,7 @@ def run_cuda_arm(args, dist: Dist):
     from covalent_ssh_plugin_b200.engine import get_engine, shutdown_all
 
     dev = dist.local_rank
-    if dist.world > 1:
+    if (dist.world > 1 and os.environ.get("B2_BENCH_BIND", "1") != "0") or os.environ.get("B2_BENCH_BIND") == "1":
         bind_to_gpu_numa(dev)
     n, payload = args.electrons, args.payload
     count = payload // 4

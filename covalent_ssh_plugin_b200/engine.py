@@ -50,7 +50,37 @@ DEFAULTS = {
     "max_batch": int(os.environ.get("B2_MAX_BATCH", 4096)),
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
     "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
+    "gc_tune": os.environ.get("B2_GC_TUNE", "1") != "0",
 }
+
+_gc_tuned = False
+
+
+def tune_gc() -> None:
+    """One-time cyclic-GC settings for a process that pushes tens of thousands of
+    electrons per second through asyncio.
+
+    Every ``run()`` allocates a task, a coroutine frame, a future callback and a
+    handful of small records; with CPython's default thresholds that is a
+    generation-0 collection every 700 allocations, and the periodic full
+    collections walk every tracked object in the process — ~150 000 more of
+    them once ``torch`` has been imported for the multi-GPU plumbing.  Measured
+    on the B200 host: 277 -> 352 ms per 10 000 electrons with torch imported,
+    all of it GC.  ``gc.freeze()`` parks what exists now in the permanent
+    generation (it is never walked again) and the young-generation threshold is
+    raised so collections happen per ~100 000 allocations.  Reference counting
+    is untouched, so ordinary objects are freed exactly as before; only
+    reference *cycles* wait a little longer.  Set B2_GC_TUNE=0 to opt out."""
+    global _gc_tuned
+    if _gc_tuned:
+        return
+    _gc_tuned = True
+    import gc
+
+    gc.collect()
+    gc.freeze()
+    g0, g1, g2 = gc.get_threshold()
+    gc.set_threshold(max(g0, 100_000), max(g1, 50), max(g2, 100))
 
 
 def _round_up(n: int, a: int = ALIGN) -> int:
@@ -235,6 +265,8 @@ class DeviceEngine:
         self.counters = {"electrons": 0, "batches": 0, "bytes_in": 0, "bytes_out": 0,
                          "zero_copy_batches": 0}
         self.closed = False
+        if c.get("gc_tune"):
+            tune_gc()
         self.heap = Heap(self.heap_base, self.heap_bytes)
         self._peer_ids: Dict[int, int] = {}
         self.sync_registry()
