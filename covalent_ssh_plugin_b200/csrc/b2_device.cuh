@@ -10,7 +10,10 @@ namespace b2 {
 
 constexpr int kWarp = 32;
 constexpr int kMoveThreads = 256;          // 8 warps per CTA in the span mover
-constexpr int kWorkerThreads = 256;        // 8 worker warps per CTA in the worker kernel
+#ifndef B2_WORKER_THREADS
+#define B2_WORKER_THREADS 256
+#endif
+constexpr int kWorkerThreads = B2_WORKER_THREADS;   // worker warps x 32 per CTA in the worker kernel
 constexpr int kCtaThreads = kWorkerThreads + kWarp;   // + 1 scheduler warp
 constexpr uint32_t kChunkBytes = 16384;    // one warp work unit in the span mover
 

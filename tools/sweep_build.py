@@ -9,6 +9,7 @@ sys.path.insert(0, str(REPO))
 from covalent_ssh_plugin_b200.build import build_variant  # noqa: E402
 
 out = REPO / "build" / "variants"
-for ctas, vec in [(4, 4), (5, 4), (6, 4), (5, 2), (6, 2), (7, 2)]:
-    p = build_variant(out / f"w{ctas}_v{vec}.so", {"B2_WORKER_MIN_CTAS": ctas, "B2_WORKER_VEC": vec})
+for threads, ctas, vec in [(256, 4, 4), (128, 8, 4), (128, 6, 4), (128, 8, 8), (64, 12, 4), (64, 16, 4), (64, 12, 8)]:
+    p = build_variant(out / f"t{threads}_w{ctas}_v{vec}.so",
+                      {"B2_WORKER_THREADS": threads, "B2_WORKER_MIN_CTAS": ctas, "B2_WORKER_VEC": vec})
     print(p)

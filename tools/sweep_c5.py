@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--wave-gib", type=float, default=8.0)
     ap.add_argument("--e2e-gib", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--payloads", default="", help="comma-separated payload bytes (default: the full list)")
+    ap.add_argument("--ns", default="1000,10000,100000")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     dev = 0
     wave_bytes = int(args.wave_gib * GiB)
@@ -79,8 +82,9 @@ def main():
     print("| payload | electrons | wave | worker M el/s | worker GB/s | of peak | pack GB/s | of peak | e2e k el/s | e2e GB/s (in+out) |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     ticket = C.c_uint64()
-    for P in PAYLOADS:
-        for N in (1000, 10000, 100000):
+    payloads = [int(x) for x in args.payloads.split(",")] if args.payloads else PAYLOADS
+    for P in payloads:
+        for N in [int(x) for x in args.ns.split(",")]:
             if N > args.max_n:
                 continue
             slot = (P + 255) & ~255
@@ -124,7 +128,7 @@ def main():
 
             e2e_cell = "-"
             e2e_gbs = "-"
-            if N * P <= args.e2e_gib * GiB and P <= 16 * MiB and N <= 10000:
+            if not args.no_e2e and N * P <= args.e2e_gib * GiB and P <= 16 * MiB and N <= 10000:
                 xs = [np.resize(noise[i::7], P // 4).copy() for i in range(min(N, 64))]
 
                 async def go():
