@@ -66,17 +66,19 @@ class DeviceElectron:
     ibeta: int = 0
 
 
-@dataclass
 class EncodedTask:
     """One electron in wire form, before arena offsets are assigned."""
 
-    spec: DeviceElectron
-    payloads: Tuple[np.ndarray, ...]   # contiguous uint8 views to stage, in operand order
-    imm: Tuple[int, int]               # immediates (int electrons)
-    count: int                         # elements per operand (bytes for K_COPY)
-    nrows: int
-    out_bytes: int
-    result_meta: tuple                 # ("array", dtype, shape, order) | ("f32",) | ("int",)
+    __slots__ = ("spec", "payloads", "imm", "count", "nrows", "out_bytes", "result_meta")
+
+    def __init__(self, spec, payloads, imm, count, nrows, out_bytes, result_meta):
+        self.spec = spec                  # DeviceElectron
+        self.payloads = payloads          # contiguous uint8 views (or DeviceRef) to stage, in operand order
+        self.imm = imm                    # immediates (int electrons)
+        self.count = count                # elements per operand (bytes for K_COPY)
+        self.nrows = nrows
+        self.out_bytes = out_bytes
+        self.result_meta = result_meta    # ("array", dtype, shape, order) | ("f32",) | ("int",)
 
 
 _lock = threading.Lock()

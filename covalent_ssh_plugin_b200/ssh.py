@@ -152,6 +152,9 @@ class CompletedElectron:
         self.stderr = stderr
 
 
+_COMPLETED_OK = CompletedElectron(0)
+
+
 class _InFlight:
     """Book-keeping for one electron between the helper calls of ``run``; keyed
     by the same artefact names the reference uses as file names."""
@@ -246,12 +249,12 @@ class SSHExecutor(RemoteExecutor):
         later steps find it.  An electron that cannot run on the device is
         recorded with the reason; ``submit_task`` reports it as a failed run.
         """
-        local, remote = self.cache_dir, self.remote_cache
-        function_file = _join(local, f"function_{operation_id}.pkl")
-        script_file = _join(local, f"exec_{operation_id}.py")
-        remote_function_file = _join(remote, f"function_{operation_id}.pkl")
-        remote_script_file = _join(remote, f"exec_{operation_id}.py")
-        remote_result_file = _join(remote, f"result_{operation_id}.pkl")
+        local, remote = _join(self.cache_dir, ""), _join(self.remote_cache, "")   # "<dir>/" prefixes
+        function_file = f"{local}function_{operation_id}.pkl"
+        script_file = f"{local}exec_{operation_id}.py"
+        remote_function_file = f"{remote}function_{operation_id}.pkl"
+        remote_script_file = f"{remote}exec_{operation_id}.py"
+        remote_result_file = f"{remote}result_{operation_id}.pkl"
 
         try:
             entry = _InFlight(encoded=encode(fn, args, kwargs))
@@ -302,11 +305,11 @@ class SSHExecutor(RemoteExecutor):
         the first one propagates.  A missing CUDA library is never retried or
         swallowed: it raises ``LibraryMissing``."""
         ordinal = resolve_device(self.hostname)
-        address = f"{self.username}@{self.hostname}"
         for attempt in range(1, self.max_connection_attempts + 1):
             try:
                 return await _open_engine(ordinal, self.hostname)
             except (ConnectionRefusedError, OSError) as err:
+                address = f"{self.username}@{self.hostname}"
                 if not self.retry_connect:
                     app_log.error(f"{err} ({address} | retry disabled).")
                     raise
@@ -363,7 +366,7 @@ class SSHExecutor(RemoteExecutor):
             raise batch.error
         status = conn.engine.status_of(staged)
         if status == _b2lib.TS_OK:
-            return CompletedElectron(0)
+            return _COMPLETED_OK
         what = {_b2lib.TS_OVERFLOW: "integer result does not fit int64",
                 _b2lib.TS_BAD_FN: "no device callback registered for this electron",
                 _b2lib.TS_BAD_ARG: "operand rejected by the device callback"}.get(status, "device error")

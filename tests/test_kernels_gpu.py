@@ -318,3 +318,44 @@ def test_dependency_chain_and_diamond(registered):
     assert list(st) == want == [M.TS_OK] * len(tasks)
     got = _read(L, dev, 0, model.size)
     assert np.array_equal(got, model)
+
+
+@pytest.mark.parametrize("seed,n,width", [(1, 500, 64), (2, 3000, 256), (3, 3000, 4), (4, 20000, 16)])
+def test_random_dags_match_the_model(registered, seed, n, width):
+    """Stress of the MPMC release logic: random DAGs (each electron reads up to two
+    earlier results), ready and dependent electrons interleaved in the table so that
+    the ready-prefix shortcut, the cursor-publishing prologue and device-side
+    successor release are all exercised under contention.  Every valid execution
+    order gives the same bytes, so the arena must equal the model's."""
+    L, dev = registered["L"], registered["dev"]
+    rng = np.random.default_rng(seed)
+    slot = (4 * width + 255) & ~255
+    n_inputs = 8
+    model = np.zeros((n_inputs + n) * slot + 256, dtype=np.uint8)
+    for i in range(n_inputs):
+        model[i * slot:i * slot + 4 * width] = rng.random(width, dtype=np.float32).view(np.uint8)
+    _write(L, dev, 0, model)
+    tasks, succ_lists = [], [[] for _ in range(n)]
+    for i in range(n):
+        out = (n_inputs + i) * slot
+        n_pred = 0 if i < 3 else int(rng.integers(0, 3))
+        preds = sorted(set(int(p) for p in rng.integers(max(0, i - 50), i, n_pred))) if n_pred else []
+        srcs = [(n_inputs + p) * slot for p in preds] + [int(rng.integers(0, n_inputs)) * slot for _ in range(2 - len(preds))]
+        if rng.random() < 0.5:
+            t = _task(3 if rng.random() < 0.5 else 4, srcs[0], srcs[1], out, width, deps=len(preds))   # add / mul
+        else:
+            t = _task(11, srcs[0], 0, out, width, deps=len(preds))                                     # -1.5x + 0.25
+            preds = preds[:1] if preds and srcs[0] == (n_inputs + preds[0]) * slot else []
+            t["deps"] = len(preds)
+        tasks.append(t)
+        for p in preds:
+            succ_lists[p].append(i)
+    succ = []
+    for i, t in enumerate(tasks):
+        t["succ_begin"], t["succ_count"] = len(succ), len(succ_lists[i])
+        succ += succ_lists[i]
+    st = _run(L, dev, tasks, succ)
+    want = M.run_tasks(model, FN, tasks, succ)
+    assert list(st) == want and all(s == M.TS_OK for s in want)
+    got = _read(L, dev, 0, model.size)
+    assert np.array_equal(got, model)
