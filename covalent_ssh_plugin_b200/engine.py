@@ -51,6 +51,11 @@ DEFAULTS = {
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
     "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
     "gc_tune": os.environ.get("B2_GC_TUNE", "1") != "0",
+    # operands of at least this many bytes are copied into pinned memory by a small
+    # thread pool (numpy releases the GIL while copying): one host thread moves
+    # ~9-11 GB/s, 8-16 threads 25-40 GB/s (tools/staging_probe.py on the B200 host)
+    "parallel_stage_bytes": int(os.environ.get("B2_PARALLEL_STAGE_BYTES", 512 * 1024)),
+    "stage_threads": int(os.environ.get("B2_STAGE_THREADS", 8)),
 }
 
 _gc_tuned = False
@@ -87,22 +92,13 @@ def _round_up(n: int, a: int = ALIGN) -> int:
     return (n + a - 1) & ~(a - 1)
 
 
-class DeviceTaskError(RuntimeError):
-    """The worker kernel reported a non-OK status for an electron."""
-
-    def __init__(self, status: int, what: str):
-        names = {L.TS_OVERFLOW: "int64 overflow", L.TS_BAD_FN: "no callback registered",
-                 L.TS_BAD_ARG: "operand outside arena or misaligned", L.TS_PENDING: "never ran"}
-        super().__init__(f"{what}: device status {status} ({names.get(status, 'unknown')})")
-        self.status = status
-
-
 class Batch:
     """Electrons staged together: one ingress segment, one egress segment, one
     launch, one future."""
 
     __slots__ = ("engine", "seg", "oseg", "n", "in_used", "out_used", "table", "future", "loop",
-                 "ticket", "unread", "done", "flushed", "error", "lease", "zero_copy", "out_freed")
+                 "ticket", "unread", "done", "flushed", "error", "lease", "zero_copy", "out_freed",
+                 "pending", "ship_wanted")
 
     def __init__(self, engine: "DeviceEngine", seg: int, oseg: int, loop):
         self.engine = engine
@@ -122,6 +118,8 @@ class Batch:
         self.lease = None           # ctypes view of the egress segment that result arrays alias
         self.zero_copy = False
         self.out_freed = False
+        self.pending = 0            # operand copies still running in the staging threads
+        self.ship_wanted = False    # flush was requested while copies were pending
 
 
 class Staged:
@@ -226,6 +224,9 @@ class DeviceEngine:
         self.max_batch = int(c["max_batch"])
         self.queue_cap = int(c["queue_cap"])
         self.zero_copy = bool(c["zero_copy"])
+        self.parallel_stage_bytes = int(c["parallel_stage_bytes"])
+        self._stage_threads = max(1, int(c["stage_threads"]))
+        self._stage_pool = None
         if self.max_batch > self.queue_cap:
             self.max_batch = self.queue_cap
         staging = int(c["staging_bytes"])
@@ -401,7 +402,30 @@ class DeviceEngine:
                 self._open = b
                 loop.call_soon(self._idle_flush, b)
             break
-        return self._append(b, enc)
+        if need_in < self.parallel_stage_bytes:
+            return self._append(b, enc, None)
+        # Large operands: reserve the space and write the task record now, let the
+        # staging threads do the copies, and hold the batch back until they are done.
+        jobs: list = []
+        staged = self._append(b, enc, jobs)
+        if jobs:
+            if self._stage_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._stage_pool = ThreadPoolExecutor(self._stage_threads, thread_name_prefix="b2-stage")
+            b.pending += 1
+            try:
+                await loop.run_in_executor(self._stage_pool, self._run_copies, jobs)
+            finally:
+                b.pending -= 1
+                if b.pending == 0 and b.ship_wanted:
+                    self._ship(b)
+        return staged
+
+    def _run_copies(self, jobs) -> None:
+        h_in = self._h_in
+        for off, p in jobs:
+            h_in[off:off + p.size] = p
 
     def _take_segments(self):
         with self._seg_lock:
@@ -409,7 +433,9 @@ class DeviceEngine:
                 return self._free_segments.pop(), self._free_out.pop()
         return None
 
-    def _append(self, b: Batch, enc: EncodedTask) -> Staged:
+    def _append(self, b: Batch, enc: EncodedTask, jobs) -> Staged:
+        """Reserve staging space, copy (or queue the copy of) the operands, write the
+        task record.  ``jobs`` collects (offset, payload) pairs instead of copying."""
         spec = enc.spec
         if spec.fn_id > self._registered:
             self.sync_registry()
@@ -420,7 +446,10 @@ class DeviceEngine:
         if len(payloads) == 1 and not enc.nrows and type(payloads[0]) is not DeviceRef:
             p = payloads[0]                               # the common case, kept short
             a0 = seg_base + b.in_used
-            h_in[a0:a0 + p.size] = p
+            if jobs is None:
+                h_in[a0:a0 + p.size] = p
+            else:
+                jobs.append((a0, p))
             b.in_used += _round_up(p.size)
             a1 = 0
         elif not payloads:
@@ -451,7 +480,10 @@ class DeviceEngine:
                         flags |= self.peer_arena_id(p.ordinal) << (L.F_ARENA0_SHIFT, L.F_ARENA1_SHIFT)[i]
                     continue
                 o = seg_base + b.in_used
-                h_in[o:o + p.size] = p
+                if jobs is None:
+                    h_in[o:o + p.size] = p
+                else:
+                    jobs.append((o, p))
                 offs.append(o)
                 b.in_used += _round_up(p.size)
             a0, a1 = offs[0], (offs[1] if len(offs) > 1 else 0)
@@ -479,7 +511,14 @@ class DeviceEngine:
             self._release_in(b.seg)
             self._release_out(b)
             return None
+        if b.pending:                  # staging threads are still filling this batch
+            b.ship_wanted = True
+            return b
+        return self._ship(b)
+
+    def _ship(self, b: Batch) -> Batch:
         b.flushed = True
+        b.ship_wanted = False
         dev = self.ordinal
         in_base = b.seg * self.seg_bytes
         out_base = b.oseg * self.seg_bytes
@@ -635,6 +674,8 @@ class DeviceEngine:
         if self.closed:
             return
         self._waitq.put(None)
+        if self._stage_pool is not None:
+            self._stage_pool.shutdown(wait=True)
         try:
             L.call("b2_sync", self.ordinal)
         finally:

@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import asyncio
 import os
-import sys
 from concurrent.futures import ProcessPoolExecutor
 from concurrent.futures.process import BrokenProcessPool
 from multiprocessing import get_context

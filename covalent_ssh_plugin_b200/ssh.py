@@ -28,7 +28,6 @@ Reference step (ssh.py)                      -> here
 from __future__ import annotations
 
 import asyncio
-import logging
 import os
 import socket
 import time

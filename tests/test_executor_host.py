@@ -537,3 +537,27 @@ def test_host_pool_is_opt_in_and_mirrors_exec_py(fake_lib, tmp_path):
         finally:
             hostpool.shutdown()
     assert not __import__("covalent_ssh_plugin_b200.ssh", fromlist=["_inflight"])._inflight
+
+
+def test_large_operands_are_staged_by_threads(fake_lib, tmp_path):
+    """Operands above the threshold are copied by the staging threads; a batch is
+    not shipped while copies into it are pending, and results stay correct."""
+    eng = engine_mod.get_engine(0, parallel_stage_bytes=64 << 10, stage_threads=4, **SMALL)
+    ex = make_executor(tmp_path)
+    n = 60
+    xs = [np.random.default_rng(i).standard_normal(20000 + 31 * i, dtype=np.float32) for i in range(n)]   # ~80 KiB each
+    ys = [np.random.default_rng(100 + i).standard_normal(20000 + 31 * i, dtype=np.float32) for i in range(n)]
+    small = [np.random.default_rng(200 + i).standard_normal(100, dtype=np.float32) for i in range(n)]
+
+    async def go():
+        big = [ex.run(electrons.vec_mul, [xs[i], ys[i]], {}, {"dispatch_id": "big", "node_id": i}) for i in range(n)]
+        tiny = [ex.run(electrons.scale_add, [small[i]], {}, {"dispatch_id": "tiny", "node_id": i}) for i in range(n)]
+        return await asyncio.gather(*big, *tiny)
+
+    out = asyncio.run(go())
+    for i in range(n):
+        assert np.array_equal(out[i], xs[i] * ys[i])
+        assert np.array_equal(out[n + i], np.float32(2.0) * small[i] + np.float32(1.0))
+    assert eng._stage_pool is not None
+    del out
+    assert sorted(eng._free_segments) == [0, 1, 2, 3]
