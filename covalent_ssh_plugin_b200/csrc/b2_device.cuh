@@ -43,6 +43,23 @@ __device__ __forceinline__ void st_stream(int4 *p, const int4 &v) {
                : "memory");
 }
 
+// ---- streaming 256-bit accessors (new on sm_100: LDG.E.256 / STG.E.256) -------
+struct alignas(32) Vec32 {
+  unsigned long long a, b, c, d;
+};
+__device__ __forceinline__ Vec32 ld_stream32(const Vec32 *p) {
+  Vec32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream32(Vec32 *p, const Vec32 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a), "l"(v.b),
+               "l"(v.c), "l"(v.d)
+               : "memory");
+}
+
 // ---- 64-bit acquire / release on queue cells --------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
   unsigned long long v;

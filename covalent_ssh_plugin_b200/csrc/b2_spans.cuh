@@ -47,11 +47,38 @@ __device__ __forceinline__ void warp_copy16(int4 *__restrict__ d, const int4 *__
   for (; i < n16; i += kWarp) st_stream(d + i, ld_stream(s + i));
 }
 
+// 256-bit flavour: UNROLL/2 x 32 lanes x 32 B per tile (same bytes in flight as the
+// 128-bit loop, half the instructions).  Pointers must be 32 B aligned.
+template <int UNROLL>
+__device__ __forceinline__ uint32_t warp_copy32(uint8_t *dst, const uint8_t *src, uint32_t len,
+                                                int lane) {
+  constexpr int U = UNROLL / 2;
+  const Vec32 *s = reinterpret_cast<const Vec32 *>(src);
+  Vec32 *d = reinterpret_cast<Vec32 *>(dst);
+  const uint32_t n32 = len >> 5;
+  uint32_t i = lane;
+  for (; i + (U - 1) * kWarp < n32; i += U * kWarp) {
+    Vec32 v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[j] = ld_stream32(s + i + j * kWarp);
+#pragma unroll
+    for (int j = 0; j < U; ++j) st_stream32(d + i + j * kWarp, v[j]);
+  }
+  for (; i < n32; i += kWarp) st_stream32(d + i, ld_stream32(s + i));
+  return n32 << 5;   // bytes handled
+}
+
 // Moves len bytes; any alignment.  16 B aligned src/dst take the vector path
 // end to end; equal misalignment peels a byte head; otherwise bytes.
-template <int UNROLL>
+template <int UNROLL, bool WIDE = false>
 __device__ __forceinline__ void warp_move(uint8_t *dst, const uint8_t *src, uint32_t len,
                                           int lane) {
+  if (WIDE && (((uintptr_t)src | (uintptr_t)dst) & 31u) == 0) {
+    const uint32_t done = warp_copy32<UNROLL>(dst, src, len, lane);
+    src += done;
+    dst += done;
+    len -= done;   // < 32 bytes left; falls through to the 128-bit / byte tail below
+  }
   const uint32_t ms = (uint32_t)((uintptr_t)src & 15u);
   const uint32_t md = (uint32_t)((uintptr_t)dst & 15u);
   if (ms != md) {  // cold path: correctness only
@@ -73,7 +100,7 @@ __device__ __forceinline__ void warp_move(uint8_t *dst, const uint8_t *src, uint
 
 // uniform_cps > 0: every span has the same byte count and therefore the same
 // number of chunks per span — the chunk -> span map is a division.
-template <int UNROLL>
+template <int UNROLL, bool WIDE = false>
 __global__ void __launch_bounds__(kMoveThreads, (UNROLL >= 16 ? 2 : (UNROLL >= 8 ? 4 : 8)))
     span_move_kernel(const SpanDev *__restrict__ spans, const uint32_t *__restrict__ chunk_base,
                      uint32_t n_spans, uint32_t n_chunks, uint32_t uniform_cps) {
@@ -101,7 +128,7 @@ __global__ void __launch_bounds__(kMoveThreads, (UNROLL >= 16 ? 2 : (UNROLL >= 8
     const uint64_t off = (uint64_t)k * kChunkBytes;
     const uint64_t rem = bytes - off;
     const uint32_t len = rem < kChunkBytes ? (uint32_t)rem : kChunkBytes;
-    warp_move<UNROLL>(dst + off, src + off, len, lane);
+    warp_move<UNROLL, WIDE>(dst + off, src + off, len, lane);
   }
 }
 

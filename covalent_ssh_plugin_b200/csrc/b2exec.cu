@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "b2_spans.cuh"
+#include "b2_spans_tma.cuh"
 #include "b2_worker.cuh"
 
 namespace {
@@ -104,6 +105,8 @@ struct Device {
   int worker_ctas_per_sm = 0;
   int mover_ctas_per_sm = 0;
   int mover_unroll = 8;
+  bool mover_tma = true;         // bulk-copy-engine kernel for 16 B aligned spans (B2_MOVER=ldg|wide to disable)
+  bool mover_wide = false;       // 256-bit loads/stores where 32 B aligned (B2_MOVER=wide)
 
   cudaEvent_t tickets[kTickets] = {};
   uint64_t next_ticket = 1;
@@ -191,6 +194,7 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   uint32_t *base = reinterpret_cast<uint32_t *>(s.h + base_off);
   uint64_t chunks = 0, moved = 0;
   bool uniform = true;
+  uint64_t misalign = 0;
   const uint64_t b0 = spans[0].bytes;
   for (uint32_t i = 0; i < n; ++i) {
     const b2_span &sp = spans[i];
@@ -210,6 +214,7 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
     base[i] = (uint32_t)chunks;
     chunks += (sp.bytes + kChunkBytes - 1) / kChunkBytes;
     moved += sp.bytes;
+    misalign |= sp.src_off | sp.dst_off | sp.bytes;
     uniform = uniform && (sp.bytes == b0);
     if (chunks > 0xFFFFFFF0ull) return fail(B2_E_NOMEM, "too many chunks in one span move");
   }
@@ -230,6 +235,14 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)cap);
   const SpanDev *dtab = reinterpret_cast<const SpanDev *>(s.d);
   const uint32_t *dbase = reinterpret_cast<const uint32_t *>(s.d + base_off);
+  if (D->mover_tma && (misalign & 15u) == 0) {
+    const uint64_t want_tma = (chunks + kTmaPipes - 1) / kTmaPipes;
+    const int grid_tma = (int)std::min<uint64_t>(want_tma, (uint64_t)D->sm_count);
+    span_move_tma_kernel<<<grid_tma, kTmaThreads, kTmaSmemBytes, D->stream>>>(dtab, dbase, n,
+                                                                              (uint32_t)chunks, cps);
+  } else if (D->mover_wide) {
+    span_move_kernel<8, true><<<grid, kMoveThreads, 0, D->stream>>>(dtab, dbase, n, (uint32_t)chunks, cps);
+  } else
   switch (D->mover_unroll) {
     case 4: launch_mover<4>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
     case 16: launch_mover<16>(D, dtab, dbase, n, (uint32_t)chunks, cps, grid); break;
@@ -353,6 +366,15 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
     default:
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->mover_ctas_per_sm, span_move_kernel<8>,
                                                        kMoveThreads, 0));
+  }
+  {
+    const char *mv = getenv("B2_MOVER");
+    // default: the bulk-copy-engine kernel whenever every span is 16 B aligned (measured
+    // +2..3 % over the register path at every payload size, profiles/r01_mover_variants.log)
+    D->mover_wide = mv && std::string(mv) == "wide";
+    D->mover_tma = !(mv && (std::string(mv) == "ldg" || std::string(mv) == "wide"));
+    CU(cudaFuncSetAttribute(span_move_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kTmaSmemBytes));
   }
   const int wcap = env_int("B2_WORKER_CTAS_PER_SM", 0);
   if (wcap > 0) D->worker_ctas_per_sm = std::min(D->worker_ctas_per_sm, wcap);
