@@ -298,6 +298,119 @@ class DeviceEngine:
             L.call("b2_read", self.ordinal, da.offset, flat.ctypes.data, da.nbytes)
         return out
 
+    # Bulk transfers of device-resident arrays: many arrays cross PCIe as ONE contiguous
+    # copy per staging segment and are scattered to / gathered from their heap slots by the
+    # span mover (K2 unpack / K1 pack) — instead of one synchronous copy per array.
+    def _take_one(self, pool: list) -> int:
+        """A free staging segment from ``pool`` (ingress or egress), waiting for in-flight
+        batches if none is free (synchronous: used by the lattice compiler, not by run())."""
+        for _ in range(3):
+            with self._seg_lock:
+                if pool:
+                    return pool.pop()
+            self.flush()
+            L.call("b2_sync", self.ordinal)
+            self._reap()
+        raise MemoryError("no free staging segment (results of earlier electrons still hold all of them)")
+
+    def _copy_into_pinned(self, jobs) -> None:
+        big = [j for j in jobs if j[1].size >= self.parallel_stage_bytes]
+        if len(big) > 1:
+            if self._stage_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._stage_pool = ThreadPoolExecutor(self._stage_threads, thread_name_prefix="b2-stage")
+            small = [j for j in jobs if j[1].size < self.parallel_stage_bytes]
+            futs = [self._stage_pool.submit(self._run_copies, [j]) for j in big]
+            self._run_copies(small)
+            for f in futs:
+                f.result()
+        else:
+            self._run_copies(jobs)
+
+    def put_many(self, arrays) -> List["DeviceArray"]:
+        """Host ndarrays -> heap slots: per staging segment one H2D + one unpack launch."""
+        out: List[DeviceArray] = []
+        flats = []
+        for a in arrays:
+            a = np.asarray(a)
+            if a.dtype != np.float32:
+                raise TypeError("device arrays are float32")
+            order = "F" if (a.flags.f_contiguous and not a.flags.c_contiguous) else "C"
+            flat = np.ascontiguousarray(a.reshape(-1, order="A" if order == "F" else "C")).view(np.uint8)
+            out.append(self.alloc(flat.size, a.shape, order))
+            flats.append(flat)
+        i, n = 0, len(flats)
+        while i < n:
+            if _round_up(flats[i].size) > self.seg_bytes:          # larger than a segment: direct copy
+                if flats[i].size:
+                    L.call("b2_write", self.ordinal, out[i].offset, flats[i].ctypes.data, flats[i].size)
+                i += 1
+                continue
+            seg = self._take_one(self._free_segments)
+            base, used, jobs, dsts, sizes = seg * self.seg_bytes, 0, [], [], []
+            while i < n and used + _round_up(flats[i].size) <= self.seg_bytes:
+                if flats[i].size:
+                    jobs.append((base + used, flats[i]))
+                    dsts.append(out[i].offset)
+                    sizes.append(flats[i].size)
+                    used += _round_up(flats[i].size)
+                i += 1
+            try:
+                if jobs:
+                    self._copy_into_pinned(jobs)
+                    L.call("b2_h2d", self.ordinal, base, base, used)
+                    d = np.array(dsts, dtype=np.uint64)
+                    z = np.array(sizes, dtype=np.uint64)
+                    L.call("b2_unpack", self.ordinal, base, d.ctypes.data, z.ctypes.data, len(d), ALIGN, None, None)
+                    L.call("b2_sync", self.ordinal)
+                    self.counters["bytes_in"] += used
+            finally:
+                self._release_in(seg)
+        return out
+
+    def get_many(self, das) -> List[np.ndarray]:
+        """Heap slots -> host ndarrays: per staging segment one pack launch + one D2H."""
+        results: List[Optional[np.ndarray]] = [None] * len(das)
+        i, n = 0, len(das)
+        cap = self.out_data_bytes
+        while i < n:
+            if _round_up(das[i].nbytes) > cap:
+                results[i] = self.get(das[i])
+                i += 1
+                continue
+            oseg = self._take_one(self._free_out)
+            base, used, idx, srcs, sizes, offs = oseg * self.seg_bytes, 0, [], [], [], []
+            while i < n and used + _round_up(das[i].nbytes) <= cap:
+                idx.append(i)
+                if das[i].nbytes:
+                    srcs.append(das[i].offset)
+                    sizes.append(das[i].nbytes)
+                offs.append(used)
+                used += _round_up(das[i].nbytes)
+                i += 1
+            try:
+                if srcs:
+                    s_ = np.array(srcs, dtype=np.uint64)
+                    z = np.array(sizes, dtype=np.uint64)
+                    L.call("b2_pack", self.ordinal, s_.ctypes.data, z.ctypes.data, len(s_),
+                           self.egress_base + base, ALIGN, None, None)
+                    L.call("b2_d2h", self.ordinal, self.egress_base + base, base, used)
+                    L.call("b2_sync", self.ordinal)
+                    self.counters["bytes_out"] += used
+                for k, j in enumerate(idx):
+                    da = das[j]
+                    arr = np.empty(da.shape, dtype=np.float32, order=da.order)
+                    if da.nbytes:
+                        flat = arr.reshape(-1, order="A" if da.order == "F" else "C")
+                        flat.view(np.uint8)[:] = self._h_out[base + offs[k]:base + offs[k] + da.nbytes]
+                    results[j] = arr
+            finally:
+                with self._seg_lock:
+                    self._free_out.append(oseg)
+                self._wake_one()
+        return results
+
     def peer_arena_id(self, other_ordinal: int) -> int:
         """Arena id under which this GPU's kernels address ``other_ordinal``'s arena
         (same-process peers; maps it on first use, b2_peer_enable)."""

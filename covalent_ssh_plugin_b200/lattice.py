@@ -186,15 +186,42 @@ def _substitute(value, values: Dict[int, Any]):
 
 
 def _materialise(value):
-    """Device-resident results become host arrays where the host needs them."""
+    """Device-resident results become host arrays where the host needs them: all of them
+    in one pack launch + one D2H per staging segment (K1), then substituted in place."""
+    found: List[DeviceArray] = []
+
+    def collect(v):
+        if isinstance(v, DeviceArray):
+            found.append(v)
+        elif isinstance(v, (list, tuple)):
+            for x in v:
+                collect(x)
+        elif isinstance(v, dict):
+            for x in v.values():
+                collect(x)
+
+    collect(value)
+    if len(found) <= 1:
+        return _materialise_one(value, {})
+    host: Dict[int, np.ndarray] = {}
+    by_engine: Dict[int, List[DeviceArray]] = {}
+    for da in found:
+        by_engine.setdefault(id(da.engine), []).append(da)
+    for das in by_engine.values():
+        for da, arr in zip(das, das[0].engine.get_many(das)):
+            host[id(da)] = arr
+    return _materialise_one(value, host)
+
+
+def _materialise_one(value, host):
     if isinstance(value, DeviceArray):
-        return value.numpy()
+        return host[id(value)] if id(value) in host else value.numpy()
     if isinstance(value, list):
-        return [_materialise(v) for v in value]
+        return [_materialise_one(v, host) for v in value]
     if isinstance(value, tuple):
-        return tuple(_materialise(v) for v in value)
+        return tuple(_materialise_one(v, host) for v in value)
     if isinstance(value, dict):
-        return {k: _materialise(v) for k, v in value.items()}
+        return {k: _materialise_one(v, host) for k, v in value.items()}
     return value
 
 
@@ -395,14 +422,38 @@ def _run_device_group(nodes, group: List[int], device, values, keep, res: Result
                 temporaries.append(p.out)
 
     # ---- pass 3: task records ---------------------------------------------------------
+    # Host operands of the whole group are uploaded first, one H2D + one unpack launch per
+    # staging segment (K2) instead of one synchronous copy per array.
+    uploaded: Dict[tuple, DeviceArray] = {}
+    pending: Dict[int, Dict[int, np.ndarray]] = {d: {} for d in engines}
+
+    def host_operands(v, dev):
+        if isinstance(v, (list, tuple)):
+            for x in v:
+                host_operands(x, dev)
+        elif type(v) is np.ndarray:
+            pending[dev].setdefault(id(v), v)
+
+    for nid in group:
+        for a in planned[nid].node.args:
+            host_operands(a, planned[nid].dev)
+    for dev, arrs in pending.items():
+        if arrs:
+            das = engines[dev].put_many(list(arrs.values()))
+            for key, da in zip(arrs, das):
+                uploaded[(dev, key)] = da
+                temporaries.append(da)
+
     def where(v, eng: DeviceEngine) -> DeviceArray:
-        """Device location of an array operand, uploading host arrays on first use."""
+        """Device location of an array operand."""
         if isinstance(v, NodeRef):
             v = planned[v.node_id].out if v.node_id in gset else values[v.node_id]
         if isinstance(v, DeviceArray):
             return v
-        da = eng.put(v)
-        temporaries.append(da)
+        da = uploaded.get((eng.ordinal, id(v)))
+        if da is None:
+            da = eng.put(v)
+            temporaries.append(da)
         return da
 
     per_dev: Dict[int, List[dict]] = {d: [] for d in engines}

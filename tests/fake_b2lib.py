@@ -159,6 +159,25 @@ class FakeLib:
         np.frombuffer((C.c_uint8 * n).from_address(_addr(dst)), dtype=np.uint8)[:] = d.arena[dev_off:dev_off + n]
         return 0
 
+    def _pack_like(self, dev, gather, scattered, sizes, n, run_off, align, out_offs, out_total):
+        d = self._dev(dev)
+        sc = np.frombuffer((C.c_uint64 * n).from_address(_addr(scattered)), dtype=np.uint64)
+        sz = np.frombuffer((C.c_uint64 * n).from_address(_addr(sizes)), dtype=np.uint64)
+        offs, total = M.pack_layout([int(x) for x in sz], int(run_off), int(align))
+        if any(int(o) + int(z) > d.arena.size for o, z in zip(sc, sz)) or run_off + total > d.arena.size:
+            return self._fail(L.B2_E_ARG, "span outside arena")
+        spans = [(int(s), o, int(z)) if gather else (o, int(s), int(z)) for s, o, z in zip(sc, offs, sz)]
+        M.move_spans(d.arena, spans)
+        d.stats["launches_pack"] += 1
+        d.stats["bytes_packed"] += int(sz.sum())
+        return 0
+
+    def b2_pack(self, dev, src_offs, sizes, n, dst_off, align, out_offs, out_total):
+        return self._pack_like(dev, True, src_offs, sizes, n, dst_off, align, out_offs, out_total)
+
+    def b2_unpack(self, dev, src_off, dst_offs, sizes, n, align, out_offs, out_total):
+        return self._pack_like(dev, False, dst_offs, sizes, n, src_off, align, out_offs, out_total)
+
     # -- callback table + queue ------------------------------------------------------
     def b2_register(self, dev, fn_id, kind, alpha, beta, ialpha, ibeta):
         self._dev(dev).fn[fn_id] = dict(kind=kind, alpha=alpha, beta=beta, ialpha=ialpha, ibeta=ibeta)

@@ -164,3 +164,43 @@ def test_overflow_in_a_dag_is_demoted_to_the_executor_decision(gpu):
     ex.run_local_on_ssh_fail = True
     r = ct.get_result(ct.dispatch(wf)(big))
     assert r.status == ct.status.COMPLETED and r.result == big + 1
+
+
+def test_bulk_upload_and_download_use_unpack_and_pack(gpu):
+    """Lattice inputs cross PCIe as one copy per staging segment + one unpack launch (K2);
+    a lattice that returns many arrays gets them back through one pack launch + one D2H (K1)."""
+    ex0 = gpu("cuda:0")
+    scale = ct.electron(E.scale_add, executor=ex0)
+    mul = ct.electron(E.vec_mul, executor=ex0)
+    rng = np.random.default_rng(8)
+    xs = [rng.random(700 + 13 * i, dtype=np.float32) for i in range(30)]
+    ws = [rng.random(700 + 13 * i, dtype=np.float32) for i in range(30)]
+
+    @ct.lattice
+    def wf(a, b):
+        return [mul(scale(a[i]), b[i]) for i in range(30)]
+
+    eng = engine_mod.existing_engine(0)
+    before = eng.stats().launches_pack
+    r = ct.get_result(ct.dispatch(wf)(xs, ws))
+    assert r.status == ct.status.COMPLETED, r.error
+    for i in range(30):
+        assert np.array_equal(r.result[i], E.vec_mul(E.scale_add(xs[i]), ws[i]))
+    assert eng.stats().launches_pack - before == 2          # one unpack (60 inputs) + one pack (30 outputs)
+    assert eng.heap.bytes_in_use() == 0 and sorted(eng._free_out) == [0, 1, 2, 3]
+
+
+def test_put_many_get_many_chunking(gpu):
+    """More bytes than one staging segment: several chunks, same values back."""
+    gpu("cuda:0")
+    eng = engine_mod.existing_engine(0)
+    rng = np.random.default_rng(9)
+    arrs = [rng.random((300 + i, 500), dtype=np.float32) for i in range(12)]      # ~7.3 MiB > 4 MiB segments
+    arrs.append(np.asfortranarray(rng.random((40, 30), dtype=np.float32)))
+    arrs.append(np.zeros(0, dtype=np.float32))
+    das = eng.put_many(arrs)
+    back = eng.get_many(das)
+    for a, b, da in zip(arrs, back, das):
+        assert b.shape == a.shape and b.flags.f_contiguous == a.flags.f_contiguous and np.array_equal(a, b)
+        da.free()
+    assert eng.heap.bytes_in_use() == 0
