@@ -385,6 +385,33 @@ def run_cuda_arm(args, dist: Dist):
 
     clk = clocks.stop()
 
+    # ---- NVLink peer path (N > 1): K4 pack into the next rank's arena ---------------------
+    peer = None
+    if dist.world > 1:
+        from covalent_ssh_plugin_b200 import distributed as D
+
+        ids = D.exchange_peer_arenas(dev, eng.arena_bytes)
+        nxt = (dist.rank + 1) % dist.world
+        m = 2000
+        rows = np.zeros((m, 3), dtype=np.uint64)
+        rows[:, 0] = heap0 + np.random.default_rng(2).permutation(m).astype(np.uint64) * payload
+        rows[:, 1] = run_off + np.arange(m, dtype=np.uint64) * payload      # contiguous in the peer's heap
+        rows[:, 2] = payload
+
+        def do_peer():
+            L.call("b2_peer_pack", dev, ids[nxt], rows.ctypes.data, m)
+
+        for _ in range(3):
+            do_peer()
+        L.call("b2_sync", dev)
+        dist.barrier()
+        ms_peer = dist.max(timed(do_peer, 10))
+        dist.barrier()
+        gbs = m * payload / 1e9 / (ms_peer / 1e3)
+        peer = {"kernel": "span mover writing into the next rank's arena (CUDA IPC mapping)",
+                "gbs_per_direction": gbs, "all_ranks_sending": True, "of_measured_peer_copy_770": gbs / 770.0,
+                "of_nominal_900": gbs / 900.0, "payloads": m, "payload_bytes": payload}
+
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if dist.world == 1 and not args.no_cpu_baseline:
@@ -413,6 +440,7 @@ def run_cuda_arm(args, dist: Dist):
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"]},
             "cpu_baseline": cpu,
+            "peer": peer,
             "device": eng.info.name.decode(),
         }
         print(json.dumps(line), flush=True)

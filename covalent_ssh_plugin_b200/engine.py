@@ -341,32 +341,48 @@ class DeviceEngine:
             out.append(self.alloc(flat.size, a.shape, order))
             flats.append(flat)
         i, n = 0, len(flats)
-        while i < n:
-            if _round_up(flats[i].size) > self.seg_bytes:          # larger than a segment: direct copy
-                if flats[i].size:
-                    L.call("b2_write", self.ordinal, out[i].offset, flats[i].ctypes.data, flats[i].size)
-                i += 1
-                continue
-            seg = self._take_one(self._free_segments)
-            base, used, jobs, dsts, sizes = seg * self.seg_bytes, 0, [], [], []
-            while i < n and used + _round_up(flats[i].size) <= self.seg_bytes:
-                if flats[i].size:
-                    jobs.append((base + used, flats[i]))
-                    dsts.append(out[i].offset)
-                    sizes.append(flats[i].size)
-                    used += _round_up(flats[i].size)
-                i += 1
-            try:
-                if jobs:
-                    self._copy_into_pinned(jobs)
-                    L.call("b2_h2d", self.ordinal, base, base, used)
-                    d = np.array(dsts, dtype=np.uint64)
-                    z = np.array(sizes, dtype=np.uint64)
-                    L.call("b2_unpack", self.ordinal, base, d.ctypes.data, z.ctypes.data, len(d), ALIGN, None, None)
-                    L.call("b2_sync", self.ordinal)
-                    self.counters["bytes_in"] += used
-            finally:
-                self._release_in(seg)
+        inflight: List[tuple] = []            # (segment, ticket): at most two, so that filling the
+                                              # next segment overlaps the previous H2D + unpack
+        def retire(limit: int) -> None:
+            while len(inflight) > limit:
+                seg_, t_ = inflight.pop(0)
+                L.call("b2_wait", self.ordinal, t_)
+                self._release_in(seg_)
+
+        try:
+            while i < n:
+                if _round_up(flats[i].size) > self.seg_bytes:          # larger than a segment: direct copy
+                    if flats[i].size:
+                        L.call("b2_write", self.ordinal, out[i].offset, flats[i].ctypes.data, flats[i].size)
+                    i += 1
+                    continue
+                retire(1)
+                seg = self._take_one(self._free_segments)
+                base, used, jobs, dsts, sizes = seg * self.seg_bytes, 0, [], [], []
+                while i < n and used + _round_up(flats[i].size) <= self.seg_bytes:
+                    if flats[i].size:
+                        jobs.append((base + used, flats[i]))
+                        dsts.append(out[i].offset)
+                        sizes.append(flats[i].size)
+                        used += _round_up(flats[i].size)
+                    i += 1
+                t = C.c_uint64()
+                try:
+                    if jobs:
+                        self._copy_into_pinned(jobs)
+                        L.call("b2_h2d", self.ordinal, base, base, used)
+                        d = np.array(dsts, dtype=np.uint64)
+                        z = np.array(sizes, dtype=np.uint64)
+                        L.call("b2_unpack", self.ordinal, base, d.ctypes.data, z.ctypes.data, len(d), ALIGN,
+                               None, None)
+                        self.counters["bytes_in"] += used
+                    L.call("b2_mark", self.ordinal, C.byref(t))
+                except BaseException:
+                    self._release_in(seg)
+                    raise
+                inflight.append((seg, t.value))
+        finally:
+            retire(0)
         return out
 
     def get_many(self, das) -> List[np.ndarray]:
