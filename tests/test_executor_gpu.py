@@ -108,10 +108,10 @@ def test_fan_out_10k_int_electrons(executor):
 
 
 def test_fan_out_64k_arrays(executor):
-    """BASELINE config 3 shape at reduced count: 2 000 x 64 KiB fp32 in/out."""
+    """BASELINE config 3 at full size: 10 000 x 64 KiB fp32 in/out, every result bit-exact."""
     from covalent_ssh_plugin_b200 import electrons
 
-    n = 2000
+    n = 10000
     xs = [np.random.default_rng([0, i]).standard_normal(16384, dtype=np.float32) for i in range(n)]
 
     async def go():
