@@ -803,6 +803,8 @@ class DeviceEngine:
         if self.closed:
             return
         self._waitq.put(None)
+        if self._waiter is not threading.current_thread():
+            self._waiter.join(timeout=10)      # it may be inside b2_wait on an event we are about to destroy
         if self._stage_pool is not None:
             self._stage_pool.shutdown(wait=True)
         try:
@@ -851,6 +853,11 @@ def shutdown_all() -> None:
             except Exception:
                 pass
         _engines.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(shutdown_all)
 
 
 def device_count() -> int:
