@@ -359,3 +359,72 @@ def test_random_dags_match_the_model(registered, seed, n, width):
     assert list(st) == want and all(s == M.TS_OK for s in want)
     got = _read(L, dev, 0, model.size)
     assert np.array_equal(got, model)
+
+
+def test_abi_housekeeping(registered):
+    """Lifecycle / error-code behaviour of the C ABI that the engine relies on."""
+    L, dev = registered["L"], registered["dev"]
+    info = L.DeviceInfo()
+    L.call("b2_get_info", dev, C.byref(info))
+    assert info.cc_major == 10 and info.sm_count >= 100 and info.abi_version == L.ABI_VERSION
+    assert info.arena_bytes == registered["arena"] and b"B200" in info.name
+    with pytest.raises(L.B2Error) as e:                       # double init
+        L.call("b2_init", dev, 1 << 20, 1 << 20, 1 << 20, 1024)
+    assert e.value.code == L.B2_E_STATE
+    with pytest.raises(L.B2Error) as e:                       # not a power of two
+        L.call("b2_init", 9, 1 << 20, 0, 0, 1000)
+    assert e.value.code == L.B2_E_ARG
+    # more electrons than the queue can hold in one launch
+    too_many = np.zeros((1 << 16) + 1, dtype=L.TASK_DTYPE)
+    with pytest.raises(L.B2Error) as e:
+        L.call("b2_enqueue", dev, too_many.ctypes.data, len(too_many), None, 0, None)
+    assert e.value.code == L.B2_E_NOMEM
+    # successor range outside the supplied list
+    bad = np.zeros(1, dtype=L.TASK_DTYPE)
+    bad["succ_begin"], bad["succ_count"] = 0, 3
+    with pytest.raises(L.B2Error) as e:
+        L.call("b2_enqueue", dev, bad.ctypes.data, 1, None, 0, None)
+    assert e.value.code == L.B2_E_ARG
+    assert L.load().b2_poll(dev, 10 ** 9) == L.B2_E_ARG                  # unknown ticket
+    # an empty launch is a valid ticket; fill + events + stats
+    t = C.c_uint64()
+    L.call("b2_launch", dev, 0, C.byref(t))
+    L.call("b2_wait", dev, t.value)
+    assert L.load().b2_poll(dev, t.value) == 0
+    s0, s1 = L.Stats(), L.Stats()
+    L.call("b2_get_stats", dev, C.byref(s0))
+    L.call("b2_fill", dev, 4096, 0xAB, 1000)
+    e0, e1 = C.c_uint32(), C.c_uint32()
+    L.call("b2_event_create", dev, C.byref(e0))
+    L.call("b2_event_create", dev, C.byref(e1))
+    L.call("b2_event_record", dev, e0.value)
+    L.call("b2_flush_l2", dev, 1 << 20, 256 << 20)
+    spans = _spans([(4096, 8192, 1000)])
+    L.call("b2_move_spans", dev, spans.ctypes.data, 1)
+    L.call("b2_event_record", dev, e1.value)
+    ms = C.c_float()
+    L.call("b2_event_elapsed_ms", dev, e0.value, e1.value, C.byref(ms))
+    assert ms.value > 0
+    assert np.all(_read(L, dev, 8192, 1000) == 0xAB)
+    L.call("b2_get_stats", dev, C.byref(s1))
+    assert s1.launches_pack == s0.launches_pack + 1 and s1.bytes_packed == s0.bytes_packed + 1000
+
+
+def test_shutdown_and_reinit(gpu_count):
+    """The 'connection' can be closed and reopened (ssh.py:585-587 / 263-268)."""
+    if gpu_count < 1:
+        pytest.skip("no CUDA device on this box")
+    from covalent_ssh_plugin_b200 import _b2lib as L
+
+    if L.load().b2_is_initialized(0):
+        pytest.skip("device 0 is held by another fixture")
+    for _ in range(3):
+        L.call("b2_init", 0, 64 << 20, 1 << 20, 1 << 20, 1024)
+        x = np.arange(1024, dtype=np.float32)
+        L.call("b2_write", 0, 0, x.ctypes.data, x.nbytes)
+        y = np.empty_like(x)
+        L.call("b2_read", 0, 0, y.ctypes.data, y.nbytes)
+        assert np.array_equal(x, y)
+        L.call("b2_shutdown", 0)
+    with pytest.raises(L.B2Error):
+        L.call("b2_sync", 0)

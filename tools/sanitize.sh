@@ -1,0 +1,11 @@
+#!/bin/bash
+# compute-sanitizer passes over the kernel-level GPU tests (small cases only).
+mkdir -p gpurun_out
+SEL='not full_size and not 20000 and not many_independent and not 1048576 and not 262145'
+for tool in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer --tool $tool"
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 99 --target-processes all \
+    python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_$tool.log 2>&1
+  echo "exit $?"
+  grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_$tool.log | tail -5
+done
