@@ -459,6 +459,9 @@ class SSHExecutor(RemoteExecutor):
 
             result, exception = await self.query_result(conn, result_file, remote_result_file)
 
+            if not self.do_cleanup and os.environ.get("B2_EMIT_ARTIFACTS", "") == "1":
+                _emit_artifacts(function_file, script_file, result_file, function, args, kwargs,
+                                result, exception)
             if self.do_cleanup:
                 released = True
                 await self.cleanup(
@@ -480,6 +483,22 @@ class SSHExecutor(RemoteExecutor):
         conn.close()
         await conn.wait_closed()
         return result
+
+
+def _emit_artifacts(function_file, script_file, result_file, fn, args, kwargs, result, exception) -> None:
+    """Compatibility mode, opt-in with B2_EMIT_ARTIFACTS=1 and
+    ``do_cleanup=False``: leave the same three local artefacts the reference leaves
+    behind (ssh.py:147-171, 451-456) — same names, same pickle formats — for tooling
+    that inspects ``cache_dir``.  Nothing on the execution path reads them."""
+    import cloudpickle
+
+    os.makedirs(os.path.dirname(function_file) or ".", exist_ok=True)
+    with open(function_file, "wb") as fh:
+        cloudpickle.dump((fn, args, kwargs), fh)
+    with open(script_file, "w", encoding="utf-8") as fh:
+        fh.write("# executed on a B200 by covalent_ssh_plugin_b200 (device callback); no script ran\n")
+    with open(result_file, "wb") as fh:
+        cloudpickle.dump((result, exception), fh)
 
 
 def _forget(conn, *names: str) -> None:

@@ -561,3 +561,24 @@ def test_large_operands_are_staged_by_threads(fake_lib, tmp_path):
     assert eng._stage_pool is not None
     del out
     assert sorted(eng._free_segments) == [0, 1, 2, 3]
+
+
+def test_artifact_compatibility_mode(fake_lib, tmp_path):
+    """do_cleanup=False + B2_EMIT_ARTIFACTS=1 leaves the reference's three local
+    artefacts (names pinned by the reference's test_file_writes) with its pickle formats."""
+    import cloudpickle
+
+    engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path, do_cleanup=False)
+    x = np.arange(64, dtype=np.float32)
+    with patch.dict(os.environ, {"B2_EMIT_ARTIFACTS": "1"}):
+        y = asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "art", "node_id": 3}))
+    names = sorted(p.name for p in tmp_path.iterdir() if "art_3" in p.name)
+    assert names == ["exec_art_3.py", "function_art_3.pkl", "result_art_3.pkl"]
+    fn, args, kwargs = cloudpickle.load(open(tmp_path / "function_art_3.pkl", "rb"))
+    assert fn is electrons.scale_add and np.array_equal(args[0], x) and kwargs == {}
+    res, exc = cloudpickle.load(open(tmp_path / "result_art_3.pkl", "rb"))
+    assert exc is None and np.array_equal(res, y)
+    # default: nothing is written
+    asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "art", "node_id": 4}))
+    assert not [p for p in tmp_path.iterdir() if "art_4" in p.name]

@@ -408,23 +408,3 @@ def test_abi_housekeeping(registered):
     assert np.all(_read(L, dev, 8192, 1000) == 0xAB)
     L.call("b2_get_stats", dev, C.byref(s1))
     assert s1.launches_pack == s0.launches_pack + 1 and s1.bytes_packed == s0.bytes_packed + 1000
-
-
-def test_shutdown_and_reinit(gpu_count):
-    """The 'connection' can be closed and reopened (ssh.py:585-587 / 263-268)."""
-    if gpu_count < 1:
-        pytest.skip("no CUDA device on this box")
-    from covalent_ssh_plugin_b200 import _b2lib as L
-
-    if L.load().b2_is_initialized(0):
-        pytest.skip("device 0 is held by another fixture")
-    for _ in range(3):
-        L.call("b2_init", 0, 64 << 20, 1 << 20, 1 << 20, 1024)
-        x = np.arange(1024, dtype=np.float32)
-        L.call("b2_write", 0, 0, x.ctypes.data, x.nbytes)
-        y = np.empty_like(x)
-        L.call("b2_read", 0, 0, y.ctypes.data, y.nbytes)
-        assert np.array_equal(x, y)
-        L.call("b2_shutdown", 0)
-    with pytest.raises(L.B2Error):
-        L.call("b2_sync", 0)
