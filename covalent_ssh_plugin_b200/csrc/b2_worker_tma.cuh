@@ -1,0 +1,332 @@
+// b2_worker_tma.cuh — K3, streaming variant: the worker kernel with its operand loads on the
+// bulk-copy engine.
+//
+// Same queue, same callback table, same successor release as worker_kernel (b2_worker.cuh).
+// What changes is who issues the loads.  In worker_kernel the worker warps load their own
+// operands, so every electron boundary (hand-off barrier, status, successor release) is a
+// bubble in that CTA's load stream — at 64 KiB per electron that costs ~15 % of HBM
+// bandwidth.  Here the scheduler warp is also the PRODUCER: it walks the electrons it claims
+// tile by tile and issues `cp.async.bulk` loads into a ring of kStages shared-memory stages,
+// running ahead ACROSS electron boundaries; the worker warps only consume full stages
+// (LDS.128 -> fp32 op -> streaming STG.128) and hand them back.  The load stream of a CTA
+// therefore never drains while there is work, whatever the workers are waiting for.
+//
+//   producer (1 thread)                                   workers (kWorkerThreads)
+//   wait empty[s] ── fill hdr[s] ── expect_tx(full[s]) ──► wait full[s]
+//   cp.async.bulk operand tile(s) -> stage[s]              read hdr[s], stage[s]; compute; STG
+//   next tile / next electron ...                          last tile: status + successors
+//                                          ◄── arrive empty[s] (one per worker warp)
+//
+// Elementwise kinds (COPY, SCALE_ADD, ADD, MUL, AXPY) stream through the ring; SUM,
+// STACK_SUM, the integer electrons and the gate electron are handed over as one "legacy"
+// stage and run the same callbacks as worker_kernel.
+#pragma once
+#include "b2_spans_tma.cuh"
+#include "b2_worker.cuh"
+
+namespace b2 {
+
+constexpr int kStages = 6;
+constexpr uint32_t kTileBytes = 4096;                 // one stage; binary electrons use 2 x 2 KiB
+constexpr uint32_t kHdrExit = 0xFFFFFFFFu;
+constexpr uint32_t kHdrLegacy = 0xFFFFFFFEu;
+constexpr uint32_t kHdrFailed = 0xFFFFFFFDu;          // status already decided by the producer
+
+struct StageHdr {
+  uint8_t *out;              // global destination of this tile
+  const uint8_t *tail0;      // global source of the < 16 B tail (last tile only)
+  const uint8_t *tail1;
+  uint32_t n_vec;            // 128-bit vectors in this tile, per operand
+  uint32_t tail_bytes;       // 0..15 bytes after the vectors (last tile only)
+  uint32_t kind;             // b2_kind of an elementwise electron, or kHdr*
+  uint32_t last;             // 1: last tile of its electron
+  uint32_t task;             // task index
+  uint32_t status;           // kHdrFailed: the status to report
+  float alpha, beta;
+  uint32_t succ_begin, succ_count;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool is_streaming_kind(uint32_t k) {
+  return k == B2_K_COPY || k == B2_K_SCALE_ADD || k == B2_K_ADD || k == B2_K_MUL || k == B2_K_AXPY;
+}
+
+__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
+    worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
+  __shared__ __align__(128) uint8_t stage_mem[kStages * kTileBytes];
+  __shared__ StageHdr hdr[kStages];
+  __shared__ Slot legacy[kStages];
+  __shared__ __align__(8) unsigned long long full_bar[kStages];
+  __shared__ __align__(8) unsigned long long empty_bar[kStages];
+  __shared__ uint32_t s_base;
+  __shared__ uint32_t s_status;
+  const uint32_t P = a.n_ready_prefix;
+  constexpr int kWorkerWarps = kWorkerThreads / kWarp;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_addr(&full_bar[s]), 1);
+      mbar_init(smem_addr(&empty_bar[s]), kWorkerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x >= kWorkerThreads) {
+    // ----------------------------------------------------------- producer warp --
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t it = 0;   // stages handed out so far
+      auto acquire = [&]() -> uint32_t {
+        const uint32_t s = it % kStages;
+        const uint32_t use = it / kStages;
+        if (use >= 1) mbar_wait(smem_addr(&empty_bar[s]), (use - 1) & 1u);
+        return s;
+      };
+      for (;;) {
+        const uint32_t ticket = queue_claim(a.q);
+        const uint32_t ti = (ticket < P) ? ticket : queue_take(a.q, ticket, a.n_tasks);
+        // a released dependent reads what other SMs just wrote with ordinary stores: order the
+        // acquire above before the copy engine's (async proxy) reads below
+        if (ticket >= P) asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (ti == kNoTask) {
+          const uint32_t s = acquire();
+          hdr[s].kind = kHdrExit;
+          mbar_arrive(smem_addr(&full_bar[s]));
+          break;
+        }
+        const b2_task t = a.tasks[ti];
+        uint32_t kind = B2_K__COUNT;
+        FnEntry fn;
+        fn.kind = 0; fn.alpha = 0.f; fn.beta = 0.f; fn.pad = 0; fn.ialpha = 0; fn.ibeta = 0;
+        if (t.fn_id < B2_MAX_FN) {
+          fn = a.fn_table[t.fn_id];
+          kind = fn.kind;
+          if (kind >= B2_K__COUNT || (kind == B2_K_NONE && t.fn_id != 0)) kind = B2_K__COUNT;
+        }
+        if (kind == B2_K__COUNT || !is_streaming_kind(kind)) {
+          // one stage carries the whole electron: bad fn_id, or a callback that reads global
+          // memory itself (SUM, STACK_SUM, integer electrons, the gate)
+          const uint32_t s = acquire();
+          StageHdr &h = hdr[s];
+          h.task = ti;
+          h.last = 1;
+          h.succ_begin = t.succ_begin;
+          h.succ_count = t.succ_count;
+          if (kind == B2_K__COUNT) {
+            h.kind = kHdrFailed;
+            h.status = B2_TS_BAD_FN;
+          } else {
+            h.kind = kHdrLegacy;
+            legacy[s].t = t;
+            legacy[s].fn = fn;
+            legacy[s].index = ti;
+            legacy[s].kind = kind;
+          }
+          mbar_arrive(smem_addr(&full_bar[s]));
+          ++it;
+          continue;
+        }
+        // ---- streaming electron: resolve once, then tile after tile -----------------
+        const bool two = (kind == B2_K_ADD || kind == B2_K_MUL || kind == B2_K_AXPY);
+        const uint64_t bytes = (kind == B2_K_COPY) ? t.count : t.count * 4;
+        bool ok = true;
+        const uint8_t *p0 = resolve(a, (t.flags >> B2_F_ARENA0_SHIFT) & 15u, t.arg0, bytes, &ok);
+        const uint8_t *p1 = two ? resolve(a, (t.flags >> B2_F_ARENA1_SHIFT) & 15u, t.arg1, bytes, &ok)
+                                : nullptr;
+        uint8_t *po = resolve(a, (t.flags >> B2_F_ARENAO_SHIFT) & 15u, t.out, bytes, &ok);
+        if ((t.flags & (B2_F_IMM0 | (two ? B2_F_IMM1 : 0u))) || !ok || !aligned16(p0) ||
+            !aligned16(po) || (two && !aligned16(p1))) {
+          const uint32_t s = acquire();
+          StageHdr &h = hdr[s];
+          h.kind = kHdrFailed;
+          h.status = B2_TS_BAD_ARG;
+          h.task = ti;
+          h.last = 1;
+          h.succ_begin = t.succ_begin;
+          h.succ_count = t.succ_count;
+          mbar_arrive(smem_addr(&full_bar[s]));
+          ++it;
+          continue;
+        }
+        const uint32_t per_tile = two ? kTileBytes / 2 : kTileBytes;
+        uint64_t off = 0;
+        do {
+          const uint64_t left = bytes - off;
+          const uint32_t chunk = left < per_tile ? (uint32_t)left : per_tile;
+          const bool last = (off + chunk == bytes);
+          const uint32_t b16 = chunk & ~15u;
+          const uint32_t s = acquire();
+          StageHdr &h = hdr[s];
+          h.out = po + off;
+          h.tail0 = p0 + off + b16;
+          h.tail1 = two ? p1 + off + b16 : nullptr;
+          h.n_vec = b16 >> 4;
+          h.tail_bytes = chunk - b16;
+          h.kind = kind;
+          h.last = last ? 1u : 0u;
+          h.task = ti;
+          h.alpha = fn.alpha;
+          h.beta = fn.beta;
+          h.succ_begin = t.succ_begin;
+          h.succ_count = t.succ_count;
+          const uint32_t fb = smem_addr(&full_bar[s]);
+          if (b16) {
+            const uint32_t dst = smem_addr(stage_mem) + s * kTileBytes;
+            mbar_expect_tx(fb, two ? 2 * b16 : b16);
+            bulk_g2s(dst, p0 + off, b16, fb);
+            if (two) bulk_g2s(dst + kTileBytes / 2, p1 + off, b16, fb);
+          } else {
+            mbar_arrive(fb);
+          }
+          ++it;
+          off += chunk;
+        } while (off < bytes);
+      }
+    }
+  } else {
+    // --------------------------------------------------------------- worker warps --
+    if (P < a.n_tasks) {   // publish ready electrons that sit behind a dependent one in the table
+      for (;;) {
+        if (threadIdx.x == 0) s_base = P + atomicAdd(a.cursor, (uint32_t)kWorkerThreads);
+        worker_sync();
+        const uint32_t base = s_base;
+        worker_sync();
+        if (base >= a.n_tasks) break;
+        const uint32_t i = base + threadIdx.x;
+        const bool ready = (i < a.n_tasks) && (a.tasks[i].deps == 0);
+        queue_push_warp(a.q, P, ready, i);
+      }
+    }
+
+    const int lane = threadIdx.x & 31;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t s = it % kStages;
+      mbar_wait(smem_addr(&full_bar[s]), (it / kStages) & 1u);
+      const StageHdr &h = hdr[s];
+      const uint32_t kind = h.kind;
+      if (kind == kHdrExit) break;
+      uint32_t status = B2_TS_OK;
+      if (kind == kHdrFailed) {
+        status = h.status;
+      } else if (kind == kHdrLegacy) {
+        const Slot &sl = legacy[s];
+        const uint32_t lk = sl.kind;
+        Ctx c;
+        bool ok = true;
+        const uint64_t arg0 = sl.t.arg0, arg1 = sl.t.arg1, count = sl.t.count;
+        const uint32_t flags = sl.t.flags, nrows = sl.t.nrows;
+        const bool is_int = (lk == B2_K_IADD || lk == B2_K_IMUL || lk == B2_K_ISCALE_ADD);
+        uint64_t in_bytes = count * 4;
+        if (lk == B2_K_STACK_SUM && nrows) in_bytes += (uint64_t)(nrows - 1) * arg1;
+        const uint64_t out_bytes = (lk == B2_K_SUM) ? 4 : (is_int ? 8 : count * 4);
+        c.imm0 = arg0;
+        c.imm1 = arg1;
+        c.a0 = ((flags & B2_F_IMM0) || is_int || lk == B2_K_NONE)
+                   ? nullptr
+                   : resolve(a, (flags >> B2_F_ARENA0_SHIFT) & 15u, arg0, in_bytes, &ok);
+        c.a1 = nullptr;
+        c.out = (lk == B2_K_NONE)
+                    ? nullptr
+                    : resolve(a, (flags >> B2_F_ARENAO_SHIFT) & 15u, sl.t.out, out_bytes, &ok);
+        c.count = count;
+        c.nrows = nrows;
+        c.fn = &sl.fn;
+        status = ok ? g_callbacks[lk](c) : (uint32_t)B2_TS_BAD_ARG;
+      } else {
+        // one tile of an elementwise electron, straight out of shared memory
+        const int4 *x = reinterpret_cast<const int4 *>(stage_mem + s * kTileBytes);
+        const int4 *y = x + (kTileBytes / 2) / 16;
+        int4 *o = reinterpret_cast<int4 *>(h.out);
+        const uint32_t n = h.n_vec;
+        const float al = h.alpha, be = h.beta;
+        for (uint32_t i = threadIdx.x; i < n; i += kWorkerThreads) {
+          int4 v = x[i];
+          if (kind != B2_K_COPY) {
+            float4 f = *reinterpret_cast<float4 *>(&v);
+            if (kind == B2_K_SCALE_ADD) {
+              f.x = __fadd_rn(__fmul_rn(al, f.x), be); f.y = __fadd_rn(__fmul_rn(al, f.y), be);
+              f.z = __fadd_rn(__fmul_rn(al, f.z), be); f.w = __fadd_rn(__fmul_rn(al, f.w), be);
+            } else {
+              int4 w = y[i];
+              const float4 g = *reinterpret_cast<float4 *>(&w);
+              if (kind == B2_K_ADD) {
+                f.x = __fadd_rn(f.x, g.x); f.y = __fadd_rn(f.y, g.y);
+                f.z = __fadd_rn(f.z, g.z); f.w = __fadd_rn(f.w, g.w);
+              } else if (kind == B2_K_MUL) {
+                f.x = __fmul_rn(f.x, g.x); f.y = __fmul_rn(f.y, g.y);
+                f.z = __fmul_rn(f.z, g.z); f.w = __fmul_rn(f.w, g.w);
+              } else {  // AXPY
+                f.x = __fadd_rn(__fmul_rn(al, f.x), g.x); f.y = __fadd_rn(__fmul_rn(al, f.y), g.y);
+                f.z = __fadd_rn(__fmul_rn(al, f.z), g.z); f.w = __fadd_rn(__fmul_rn(al, f.w), g.w);
+              }
+            }
+            v = *reinterpret_cast<int4 *>(&f);
+          }
+          st_stream(o + i, v);
+        }
+        // < 16 trailing bytes of the electron: read from global, element by element
+        const uint32_t tb = h.tail_bytes;
+        if (tb && threadIdx.x < (kind == B2_K_COPY ? tb : tb / 4)) {
+          uint8_t *ot = h.out + (n << 4);
+          if (kind == B2_K_COPY) {
+            ot[threadIdx.x] = h.tail0[threadIdx.x];
+          } else {
+            const float xv = reinterpret_cast<const float *>(h.tail0)[threadIdx.x];
+            float r;
+            if (kind == B2_K_SCALE_ADD) {
+              r = __fadd_rn(__fmul_rn(al, xv), be);
+            } else {
+              const float yv = reinterpret_cast<const float *>(h.tail1)[threadIdx.x];
+              r = (kind == B2_K_ADD) ? __fadd_rn(xv, yv)
+                  : (kind == B2_K_MUL) ? __fmul_rn(xv, yv)
+                                       : __fadd_rn(__fmul_rn(al, xv), yv);
+            }
+            reinterpret_cast<float *>(ot)[threadIdx.x] = r;
+          }
+        }
+      }
+
+      if (h.last) {
+        const uint32_t ti = h.task, succ_begin = h.succ_begin, succ_count = h.succ_count;
+        if (threadIdx.x == 0) s_status = status;
+        worker_sync();  // every result store of this electron is ordered before what follows
+        if (threadIdx.x == 0) a.status[ti] = s_status;
+        for (uint32_t base = 0; base < succ_count; base += kWorkerThreads) {
+          const uint32_t e = base + threadIdx.x;
+          bool fire = false;
+          uint32_t sidx = 0;
+          if (e < succ_count) {
+            sidx = a.succ[succ_begin + e];
+            if (sidx < a.n_tasks) {
+              __threadfence();
+              fire = (atomicSub(&a.tasks[sidx].deps, 1u) == kDepBias + 1u);
+            }
+          }
+          queue_push_warp(a.q, P, fire, sidx);
+        }
+      }
+      // hand the stage back: one arrival per worker warp, after the whole warp has read it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
+    }
+  }
+
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.exited, 1u) == gridDim.x - 1) {
+      *a.q.head = 0;
+      *a.q.tail = 0;
+      *a.cursor = 0;
+      *a.exited = 0;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace b2

@@ -25,6 +25,7 @@
 #include "b2_spans.cuh"
 #include "b2_spans_tma.cuh"
 #include "b2_worker.cuh"
+#include "b2_worker_tma.cuh"
 
 namespace {
 
@@ -107,6 +108,7 @@ struct Device {
   int mover_unroll = 8;
   bool mover_tma = true;         // bulk-copy-engine kernel for 16 B aligned spans (B2_MOVER=ldg|wide to disable)
   bool mover_wide = false;       // 256-bit loads/stores where 32 B aligned (B2_MOVER=wide)
+  bool worker_tma = true;        // streaming worker, operand loads on the copy engine (B2_WORKER=classic to disable)
 
   cudaEvent_t tickets[kTickets] = {};
   uint64_t next_ticket = 1;
@@ -350,8 +352,19 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   D->next_ticket = 1;
   D->n_user_ev = 0;
 
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_kernel,
-                                                   kCtaThreads, 0));
+  {
+    const char *wk = getenv("B2_WORKER");
+    // default: the streaming worker (operand loads on the copy engine); B2_WORKER=classic
+    // selects worker_kernel, whose worker warps load their own operands
+    D->worker_tma = !(wk && std::string(wk) == "classic");
+    CU(cudaFuncSetAttribute(worker_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
+  if (D->worker_tma)
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_tma_kernel,
+                                                     kCtaThreads, 0));
+  else
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_kernel,
+                                                     kCtaThreads, 0));
   D->mover_unroll = env_int("B2_MOVER_UNROLL", 8);
   if (D->mover_unroll != 4 && D->mover_unroll != 16) D->mover_unroll = 8;
   switch (D->mover_unroll) {
@@ -721,7 +734,10 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   }
   const int cap = D->sm_count * std::max(1, D->worker_ctas_per_sm);
   const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
-  worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
+  if (D->worker_tma)
+    worker_tma_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
+  else
+    worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
   CU(cudaGetLastError());
   // the slot (pinned table + device mirror) is reusable once this kernel is done
   CU(cudaEventRecord(s.ev, D->stream));

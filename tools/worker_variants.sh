@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs on the GPU box: correctness + rates for the classic and the TMA-streaming worker.
+for w in classic tma; do
+  echo "== B2_WORKER=$w"
+  B2_WORKER=$w timeout -s KILL 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+  B2_WORKER=$w timeout -s KILL 200 python bench.py --steps 10 --warmup 3 --skip-e2e --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for line in sys.stdin:
+    try: d = json.loads(line)
+    except Exception: print(line.rstrip()[:200]); continue
+    k = d['kernels']
+    print('64KiB step_ms %.3f worker %.0f GB/s (%.3f)' % (d['ms_per_step'], k['worker']['achieved_gbs'], k['worker']['frac']))
+"
+  B2_WORKER=$w timeout -s KILL 300 python tools/sweep_c5.py --payloads 1024,16384,65536,262144,1048576,16777216 --ns 10000 --no-e2e --wave-gib 4 2>&1 | grep -E "^\| [0-9]" | cut -d'|' -f2,3,5,6,7
+done
