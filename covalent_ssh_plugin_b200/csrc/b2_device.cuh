@@ -11,7 +11,7 @@ namespace b2 {
 constexpr int kWarp = 32;
 constexpr int kMoveThreads = 256;          // 8 warps per CTA in the span mover
 #ifndef B2_WORKER_THREADS
-#define B2_WORKER_THREADS 128
+#define B2_WORKER_THREADS 256
 #endif
 constexpr int kWorkerThreads = B2_WORKER_THREADS;   // worker warps x 32 per CTA in the worker kernel
 constexpr int kCtaThreads = kWorkerThreads + kWarp;   // + 1 scheduler warp

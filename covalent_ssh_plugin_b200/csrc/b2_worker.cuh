@@ -67,10 +67,10 @@ struct Ctx {
 typedef uint32_t (*callback_t)(const Ctx &);   // returns a b2_task_status; called by all threads
 
 #ifndef B2_WORKER_VEC
-#define B2_WORKER_VEC 8
+#define B2_WORKER_VEC 4
 #endif
 #ifndef B2_WORKER_MIN_CTAS
-#define B2_WORKER_MIN_CTAS 8
+#define B2_WORKER_MIN_CTAS 4
 #endif
 constexpr int kVec = B2_WORKER_VEC;  // 128-bit vectors in flight per thread
 
@@ -341,7 +341,7 @@ struct Slot {
   uint32_t kind;    // validated b2_kind, or B2_K__COUNT for "bad fn_id"
 };
 
-// One CTA = 4 worker warps + 1 scheduler warp (B2_WORKER_THREADS / 32 worker warps; 8 CTAs per SM).  The scheduler runs one electron
+// One CTA = B2_WORKER_THREADS / 32 (8) worker warps + 1 scheduler warp, 4 CTAs per SM.  The scheduler runs one electron
 // ahead: while the workers stream electron k it claims the next ticket, waits
 // for that cell to be published if it is a released dependent, and stages the
 // task record and its callback-table entry in shared memory, so the L2 round

@@ -6,7 +6,7 @@
 // operands, so every electron boundary (hand-off barrier, status, successor release) is a
 // bubble in that CTA's load stream — at 64 KiB per electron that costs ~15 % of HBM
 // bandwidth.  Here the scheduler warp is also the PRODUCER: it walks the electrons it claims
-// tile by tile and issues `cp.async.bulk` loads into a ring of kStages shared-memory stages,
+// tile by tile (16 KiB) and issues `cp.async.bulk` loads into a ring of kStages (3) shared-memory stages,
 // running ahead ACROSS electron boundaries; the worker warps only consume full stages
 // (LDS.128 -> fp32 op -> streaming STG.128) and hand them back.  The load stream of a CTA
 // therefore never drains while there is work, whatever the workers are waiting for.
@@ -26,8 +26,15 @@
 
 namespace b2 {
 
-constexpr int kStages = 6;
-constexpr uint32_t kTileBytes = 4096;                 // one stage; binary electrons use 2 x 2 KiB
+#ifndef B2_TMA_STAGES
+#define B2_TMA_STAGES 3
+#endif
+#ifndef B2_TMA_TILE
+#define B2_TMA_TILE 16384
+#endif
+constexpr int kStages = B2_TMA_STAGES;
+constexpr uint32_t kTileBytes = B2_TMA_TILE;          // one stage; binary electrons use two halves
+constexpr uint32_t kWorkerSmemBytes = kStages * kTileBytes;
 constexpr uint32_t kHdrExit = 0xFFFFFFFFu;
 constexpr uint32_t kHdrLegacy = 0xFFFFFFFEu;
 constexpr uint32_t kHdrFailed = 0xFFFFFFFDu;          // status already decided by the producer
@@ -56,7 +63,7 @@ __device__ __forceinline__ bool is_streaming_kind(uint32_t k) {
 
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
-  __shared__ __align__(128) uint8_t stage_mem[kStages * kTileBytes];
+  extern __shared__ __align__(128) uint8_t stage_mem[];   // kStages x kTileBytes, dynamic
   __shared__ StageHdr hdr[kStages];
   __shared__ Slot legacy[kStages];
   __shared__ __align__(8) unsigned long long full_bar[kStages];

@@ -358,10 +358,12 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
     // selects worker_kernel, whose worker warps load their own operands
     D->worker_tma = !(wk && std::string(wk) == "classic");
     CU(cudaFuncSetAttribute(worker_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(worker_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kWorkerSmemBytes));
   }
   if (D->worker_tma)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_tma_kernel,
-                                                     kCtaThreads, 0));
+                                                     kCtaThreads, kWorkerSmemBytes));
   else
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_kernel,
                                                      kCtaThreads, 0));
@@ -735,7 +737,7 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   const int cap = D->sm_count * std::max(1, D->worker_ctas_per_sm);
   const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
   if (D->worker_tma)
-    worker_tma_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
+    worker_tma_kernel<<<grid, kCtaThreads, kWorkerSmemBytes, D->stream>>>(a);
   else
     worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
   CU(cudaGetLastError());

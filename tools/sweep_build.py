@@ -9,7 +9,9 @@ sys.path.insert(0, str(REPO))
 from covalent_ssh_plugin_b200.build import build_variant  # noqa: E402
 
 out = REPO / "build" / "variants"
-for threads, ctas, vec in [(256, 4, 4), (128, 8, 4), (128, 6, 4), (128, 8, 8), (64, 12, 4), (64, 16, 4), (64, 12, 8)]:
-    p = build_variant(out / f"t{threads}_w{ctas}_v{vec}.so",
-                      {"B2_WORKER_THREADS": threads, "B2_WORKER_MIN_CTAS": ctas, "B2_WORKER_VEC": vec})
+for threads, ctas, stages, tile in [(256, 4, 3, 16384), (256, 3, 4, 16384), (256, 2, 3, 32768), (128, 4, 3, 16384),
+                                    (512, 2, 6, 16384), (256, 3, 2, 32768)]:
+    p = build_variant(out / f"t{threads}_w{ctas}_s{stages}_tile{tile}.so",
+                      {"B2_WORKER_THREADS": threads, "B2_WORKER_MIN_CTAS": ctas, "B2_TMA_STAGES": stages,
+                       "B2_TMA_TILE": tile})
     print(p)
