@@ -40,6 +40,8 @@ _TASK = struct.Struct("<IIQQQQIIIIQ")
 assert _TASK.size == 64
 
 ALIGN = 256                      # payload alignment inside a segment
+SPLIT_BYTES = 1 << 20            # large elementwise electrons are sliced into tasks of this size
+_ELEMENTWISE = (L.K_COPY, L.K_SCALE_ADD, L.K_ADD, L.K_MUL, L.K_AXPY)
 MiB = 1 << 20
 
 DEFAULTS = {
@@ -125,12 +127,13 @@ class Batch:
 class Staged:
     """Handle of one staged electron (what the executor keeps between steps)."""
 
-    __slots__ = ("batch", "index", "out_off", "out_bytes", "meta", "spec")
+    __slots__ = ("batch", "index", "out_off", "out_bytes", "meta", "spec", "parts")
 
     def __init__(self, batch: Batch, index: int, out_off: int, out_bytes: int, meta: tuple,
                  spec: DeviceElectron):
         self.batch = batch
         self.index = index
+        self.parts = 1                  # task records this electron occupies (large ones are sliced)
         self.out_off = out_off          # byte offset inside the batch's egress segment
         self.out_bytes = out_bytes
         self.meta = meta
@@ -619,12 +622,39 @@ class DeviceEngine:
         out_off = b.out_used                                 # inside the egress segment
         b.out_used = out_off + _round_up(max(enc.out_bytes, 16))
         idx = b.n
-        _TASK.pack_into(b.table, idx * 64, spec.fn_id, flags, a0, a1,
-                        self.egress_base + b.oseg * self.seg_bytes + out_off, enc.count, enc.nrows,
-                        0, 0, 0, 0)
-        b.n = idx + 1
+        out_dev = self.egress_base + b.oseg * self.seg_bytes + out_off
+        parts = 1
+        if enc.out_bytes >= 2 * SPLIT_BYTES and spec.kind in _ELEMENTWISE and not (flags & L.F_IMM0):
+            # One electron = one CTA on the device.  A batch of a few very large electrons would
+            # leave most of the 592 resident CTAs idle, so a large elementwise electron goes out
+            # as 1 MiB slices (disjoint ranges of the same operands); it has succeeded when every
+            # slice has.
+            esz = 1 if spec.kind == L.K_COPY else 4
+            total = enc.count
+            per = SPLIT_BYTES // esz
+            parts = min(-(-total // per), self.max_batch - idx)
+            if parts > 1:
+                per = -(-total // parts)
+                per = (per + 63) & ~63                       # keep slice starts 256 B aligned
+                two = spec.kind in (L.K_ADD, L.K_MUL, L.K_AXPY)
+                done, k = 0, 0
+                while done < total:
+                    n_el = min(per, total - done)
+                    o = done * esz
+                    _TASK.pack_into(b.table, (idx + k) * 64, spec.fn_id, flags, a0 + o,
+                                    (a1 + o) if two else a1, out_dev + o, n_el, 0, 0, 0, 0, 0)
+                    done += n_el
+                    k += 1
+                parts = k
+        if parts <= 1:
+            parts = 1
+            _TASK.pack_into(b.table, idx * 64, spec.fn_id, flags, a0, a1, out_dev, enc.count, enc.nrows,
+                            0, 0, 0, 0)
+        b.n = idx + parts
         b.unread += 1
-        return Staged(b, idx, out_off, enc.out_bytes, enc.result_meta, spec)
+        st = Staged(b, idx, out_off, enc.out_bytes, enc.result_meta, spec)
+        st.parts = parts
+        return st
 
     def _idle_flush(self, b: Batch) -> None:
         if self._open is b and not b.flushed:
@@ -725,7 +755,11 @@ class DeviceEngine:
     def status_of(self, s: Staged) -> int:
         b = s.batch
         off = b.oseg * self.seg_bytes + self.out_data_bytes + 4 * s.index
-        return int(self._h_out[off:off + 4].view(np.uint32)[0])
+        if s.parts == 1:
+            return int(self._h_out[off:off + 4].view(np.uint32)[0])
+        words = self._h_out[off:off + 4 * s.parts].view(np.uint32)
+        bad = words[words != L.TS_OK]
+        return int(bad[0]) if len(bad) else L.TS_OK
 
     def result_of(self, s: Staged) -> Any:
         """Materialise one result (ssh.py:451-456).  Array results alias the

@@ -582,3 +582,20 @@ def test_artifact_compatibility_mode(fake_lib, tmp_path):
     # default: nothing is written
     asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "art", "node_id": 4}))
     assert not [p for p in tmp_path.iterdir() if "art_4" in p.name]
+
+
+def test_large_elementwise_electrons_are_sliced(fake_lib, tmp_path):
+    """A 5 MiB electron goes to the device as 1 MiB slices (so that a handful of huge
+    electrons still occupy every CTA); results and failure reporting are unchanged."""
+    eng = engine_mod.get_engine(0, arena_bytes=160 << 20, staging_bytes=64 << 20, n_segments=4, max_batch=64,
+                                queue_cap=256)
+    ex = make_executor(tmp_path)
+    n = (5 << 20) // 4 + 37                                   # not a multiple of anything convenient
+    x = np.random.default_rng(0).standard_normal(n, dtype=np.float32)
+    y = np.random.default_rng(1).standard_normal(n, dtype=np.float32)
+    before = eng.counters["electrons"]
+    out = asyncio.run(ex.run(electrons.axpy_half, [x, y], {}, {"dispatch_id": "big", "node_id": 0}))
+    assert np.array_equal(out, np.float32(0.5) * x + y)
+    assert eng.counters["electrons"] - before >= 5            # task records, one per slice
+    z = asyncio.run(ex.run(electrons.identity, [x], {}, {"dispatch_id": "big", "node_id": 1}))
+    assert np.array_equal(z, x)
