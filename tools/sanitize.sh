@@ -9,3 +9,9 @@ for tool in memcheck racecheck synccheck; do
   echo "exit $?"
   grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_$tool.log | tail -5
 done
+# the classic worker (named barriers only) is what racecheck can verify end to end
+echo "== compute-sanitizer --tool racecheck  (B2_WORKER=classic B2_MOVER=ldg)"
+B2_WORKER=classic B2_MOVER=ldg timeout 900 compute-sanitizer --tool racecheck --error-exitcode 99 --target-processes all \
+  python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_racecheck_classic.log 2>&1
+echo "exit $?"
+grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/sanitize_racecheck_classic.log | tail -3
