@@ -538,6 +538,9 @@ def _run_device_group(nodes, group: List[int], device, values, keep, res: Result
 
     # ---- pass 4: launch ------------------------------------------------------------------
     single = len(engines) == 1
+    import time as _time
+
+    t_launch = _time.perf_counter()
     if single:
         dev = next(iter(engines))
         st = _launch(engines[dev], per_dev[dev], None)
@@ -568,6 +571,8 @@ def _run_device_group(nodes, group: List[int], device, values, keep, res: Result
                 _check(st, [per_dev[dev][i] for i in sorted(idxs)])
                 res.stats["device_batches"] += 1
     res.stats["device_electrons"] += len(group)
+    res.stats["device_tasks"] = res.stats.get("device_tasks", 0) + sum(len(v) for v in per_dev.values())
+    res.stats["dag_seconds"] = res.stats.get("dag_seconds", 0.0) + (_time.perf_counter() - t_launch)
 
     # ---- results ---------------------------------------------------------------------------
     for nid in group:
