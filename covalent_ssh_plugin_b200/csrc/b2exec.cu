@@ -74,6 +74,9 @@ struct Device {
   int sm_count = 0;
   cudaStream_t stream = nullptr;         // compute: every kernel and payload copy, in call order
   cudaStream_t upload = nullptr;         // task tables only, so table k+1 uploads while kernel k runs
+  cudaStream_t egress = nullptr;         // device->host copies: D2H of batch k overlaps H2D of batch k+1
+  cudaEvent_t to_egress = nullptr;       // compute -> egress ordering point
+  bool egress_dirty = false;             // copies queued on the egress stream since the last ticket
 
   uint8_t *h_in = nullptr, *h_out = nullptr;
   uint64_t h_in_bytes = 0, h_out_bytes = 0;
@@ -91,7 +94,6 @@ struct Device {
   uint32_t qcap = 0;
   uint32_t epoch = 0;
   FnEntry *d_fn = nullptr;
-  uint32_t *d_status = nullptr;
 
   // pending batch: [qcap tasks][succ_cap successor indices]
   Staging task_ring[kRing];
@@ -258,6 +260,14 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   return B2_OK;
 }
 
+// Everything issued on the compute stream so far happens before whatever is queued on the
+// egress stream next.
+int egress_after_compute(Device *D) {
+  CU(cudaEventRecord(D->to_egress, D->stream));
+  CU(cudaStreamWaitEvent(D->egress, D->to_egress, 0));
+  return B2_OK;
+}
+
 int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   if (!v || !*v) return dflt;
@@ -314,6 +324,9 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   D->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&D->upload, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&D->egress, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&D->to_egress, cudaEventDisableTiming));
+  D->egress_dirty = false;
 
   CU(cudaMalloc(reinterpret_cast<void **>(&D->arena[0]), arena_bytes));
   D->arena_bytes[0] = arena_bytes;
@@ -338,7 +351,6 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   D->d_exited = D->d_head + 48;
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_fn), sizeof(FnEntry) * B2_MAX_FN));
   CU(cudaMemsetAsync(D->d_fn, 0, sizeof(FnEntry) * B2_MAX_FN, D->stream));
-  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_status), (size_t)queue_cap * 4));
   queue_init_kernel<<<(queue_cap + 255) / 256, 256, 0, D->stream>>>(D->d_cells, queue_cap,
                                                                    D->d_head);
   CU(cudaGetLastError());
@@ -399,7 +411,8 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   // Size every staging slot up front so that steady-state calls never allocate
   // (cudaHostAlloc / cudaMalloc synchronise the device).
   for (auto &s : D->task_ring) {
-    int rc = staging_reserve(s, (size_t)queue_cap * sizeof(b2_task) + (size_t)D->succ_cap * 4);
+    int rc = staging_reserve(s, (size_t)queue_cap * sizeof(b2_task) + (size_t)D->succ_cap * 4 +
+                                    (size_t)queue_cap * 4);
     if (rc) return rc;
   }
   for (auto &s : D->span_ring) {
@@ -421,6 +434,7 @@ int b2_shutdown(int dev) {
   cudaSetDevice(dev);
   cudaStreamSynchronize(D->upload);
   cudaStreamSynchronize(D->stream);
+  cudaStreamSynchronize(D->egress);
   for (int i = 1; i < D->n_arenas; ++i)
     if (D->arena_ipc[i] && D->arena[i]) cudaIpcCloseMemHandle(D->arena[i]);
   for (auto &s : D->task_ring) staging_free(s);
@@ -435,9 +449,10 @@ int b2_shutdown(int dev) {
   cudaFree(D->d_cells);
   cudaFree(D->d_head);
   cudaFree(D->d_fn);
-  cudaFree(D->d_status);
   cudaStreamDestroy(D->stream);
   cudaStreamDestroy(D->upload);
+  cudaStreamDestroy(D->egress);
+  if (D->to_egress) { cudaEventDestroy(D->to_egress); D->to_egress = nullptr; }
   for (int i = 0; i < B2_MAX_ARENAS; ++i) {
     D->arena[i] = nullptr;
     D->arena_bytes[i] = 0;
@@ -540,8 +555,11 @@ int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes) {
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "d2h: device range outside arena");
   if (!bytes) return B2_OK;
+  int rc = egress_after_compute(D);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(D->h_out + host_off, D->arena[0] + dev_off, bytes, cudaMemcpyDeviceToHost,
-                     D->stream));
+                     D->egress));
+  D->egress_dirty = true;
   D->stats.bytes_d2h += bytes;
   return B2_OK;
 }
@@ -653,7 +671,7 @@ int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, 
   Staging &s = D->task_ring[D->task_slot];
   const size_t succ_off = (size_t)D->qcap * sizeof(b2_task);
   if (D->pend_tasks == 0 && D->pend_succ == 0) {
-    int rc = staging_reserve(s, succ_off + (size_t)D->succ_cap * 4);
+    int rc = staging_reserve(s, succ_off + (size_t)D->succ_cap * 4 + (size_t)D->qcap * 4);
     if (rc) return rc;
   }
   if (first_index) *first_index = D->pend_tasks;
@@ -689,7 +707,15 @@ static int record_ticket(Device *D, uint64_t *ticket) {
   const uint64_t t = D->next_ticket++;
   cudaEvent_t &ev = D->tickets[t % kTickets];
   if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CU(cudaEventRecord(ev, D->stream));
+  if (D->egress_dirty) {
+    // the ticket covers the compute stream AND the copies queued on the egress stream
+    int rc = egress_after_compute(D);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev, D->egress));
+    D->egress_dirty = false;
+  } else {
+    CU(cudaEventRecord(ev, D->stream));
+  }
   if (ticket) *ticket = t;
   return B2_OK;
 }
@@ -718,7 +744,10 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   memset(&a, 0, sizeof a);
   a.tasks = reinterpret_cast<b2_task *>(s.d);
   a.succ = reinterpret_cast<const uint32_t *>(s.d + succ_off);
-  a.status = D->d_status;
+  // status words live in the slot's own device buffer: the copy of batch k's statuses runs on
+  // the egress stream while kernel k+1 (another slot) is already writing its own
+  uint32_t *slot_status = reinterpret_cast<uint32_t *>(s.d + succ_off + (size_t)D->succ_cap * 4);
+  a.status = slot_status;
   a.fn_table = D->d_fn;
   a.q.cells = D->d_cells;
   a.q.head = D->d_head;
@@ -741,14 +770,19 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   else
     worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
   CU(cudaGetLastError());
-  // the slot (pinned table + device mirror) is reusable once this kernel is done
-  CU(cudaEventRecord(s.ev, D->stream));
+  // the slot (pinned table + device mirror + status words) is reusable once this kernel — and the
+  // status copy below, if any — is done
+  if (status_host_off == UINT64_MAX) CU(cudaEventRecord(s.ev, D->stream));
   s.in_flight = true;
   D->stats.launches_worker += 1;
   D->stats.electrons += n;
   if (status_host_off != UINT64_MAX) {
-    CU(cudaMemcpyAsync(D->h_out + status_host_off, D->d_status, (size_t)n * 4,
-                       cudaMemcpyDeviceToHost, D->stream));
+    int rc_ = egress_after_compute(D);
+    if (rc_) return rc_;
+    CU(cudaMemcpyAsync(D->h_out + status_host_off, slot_status, (size_t)n * 4, cudaMemcpyDeviceToHost,
+                       D->egress));
+    CU(cudaEventRecord(s.ev, D->egress));
+    D->egress_dirty = true;
     D->stats.bytes_d2h += (uint64_t)n * 4;
   }
   D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
@@ -790,12 +824,16 @@ int b2_wait(int dev, uint64_t ticket) {
 }
 
 int b2_sync(int dev) {
-  cudaStream_t st;
+  cudaStream_t st, up, eg;
   {
     DEV_OR_FAIL(D, dev);
     st = D->stream;
+    up = D->upload;
+    eg = D->egress;
   }
+  CU(cudaStreamSynchronize(up));
   CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(eg));
   return B2_OK;
 }
 

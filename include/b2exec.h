@@ -29,9 +29,14 @@
  *     device; every device address in this ABI is a BYTE OFFSET into that arena.
  *   - the caller owns host buffers; the library owns the device arena, the
  *     pinned staging buffers, streams, events and the device-side queue.
- *   - work is stream-ordered per device: calls enqueue asynchronously on the
- *     device's compute stream in call order; b2_sync / b2_wait / b2_poll are
- *     the only blocking/observing calls.
+ *   - work is stream-ordered per device: calls enqueue asynchronously in call
+ *     order; b2_sync / b2_wait / b2_poll are the only blocking/observing calls.
+ *     Device->host copies (b2_d2h, the status words of b2_launch) run on their
+ *     own stream so that the download of one batch overlaps the upload of the
+ *     next: such a copy starts after everything issued before it, but calls
+ *     issued AFTER it do not wait for it.  A ticket (b2_launch / b2_mark) taken
+ *     after the copy completes only when the copy has — do not overwrite the
+ *     copy's source before such a ticket has completed.
  */
 #ifndef B2EXEC_H
 #define B2EXEC_H
