@@ -171,6 +171,12 @@ def cpu_baseline_sample(n_sample: int, payload: int, steps: int = 1, warmup: int
     times = []
     with tempfile.TemporaryDirectory(prefix="b2-cpu-") as tmp:
         s = P.PortSettings(tmp, pythonpath=str(REPO))
+        # One BLAS/OpenMP thread per remote interpreter: with `cores` interpreters in flight the
+        # default (one thread pool of `cores` threads EACH) oversubscribes the host ~cores-fold and
+        # makes the reference path ~10x slower (15 vs 150 electrons/s on the 128-core B200 host).
+        # The baseline is timed in its best configuration.
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            s.env[var] = "1"
         for it in range(warmup + steps):
             t0 = time.perf_counter()
             out = asyncio.run(P.run_many(s, calls, cores))
@@ -181,7 +187,8 @@ def cpu_baseline_sample(n_sample: int, payload: int, steps: int = 1, warmup: int
     dt = sum(times) / len(times)
     return {"value": n_sample / dt, "unit": "electrons/s", "cores": cores, "kind": "port",
             "sample": f"{n_sample} electrons x {payload} B fp32 scale_add through oracle/reference_port.py "
-                      f"(reference ssh.py+exec.py path, local transport), waves of {cores} coroutines",
+                      f"(reference ssh.py+exec.py path, local transport), waves of {cores} coroutines, "
+                      f"OMP/BLAS threads pinned to 1 per remote interpreter",
             "seconds": dt}, times
 
 
