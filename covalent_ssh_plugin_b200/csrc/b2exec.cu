@@ -13,6 +13,7 @@
 // small event-guarded pinned rings so that calls never block on the GPU unless
 // the ring wraps.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
 #include <cstdarg>
@@ -267,6 +268,12 @@ int egress_after_compute(Device *D) {
   CU(cudaStreamWaitEvent(D->egress, D->to_egress, 0));
   return B2_OK;
 }
+
+// NVTX range around the host side of an ABI call (visible to ncu --nvtx / nsys).
+struct Range {
+  explicit Range(const char *name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
 
 int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -597,6 +604,7 @@ int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
 
 // ----------------------------------------------------------- pack / unpack --
 int b2_move_spans(int dev, const b2_span *spans, uint32_t n) {
+  Range r_("b2_move_spans");
   DEV_OR_FAIL(D, dev);
   return move_spans_locked(D, spans, n, 0, 0);
 }
@@ -606,6 +614,7 @@ static int pack_like(int dev, bool gather, const uint64_t *scattered, const uint
                      uint64_t *out_total) {
   if (n && (!scattered || !sizes)) return fail(B2_E_ARG, "offsets/sizes is NULL");
   if (align == 0 || (align & (align - 1))) return fail(B2_E_ARG, "align must be a power of two");
+  Range r_(gather ? "b2_pack" : "b2_unpack");
   DEV_OR_FAIL(D, dev);
   std::vector<b2_span> spans(n);
   uint64_t cur = run_off;
@@ -721,6 +730,7 @@ static int record_ticket(Device *D, uint64_t *ticket) {
 }
 
 int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
+  Range r_("b2_launch");
   DEV_OR_FAIL(D, dev);
   const uint32_t n = D->pend_tasks;
   if (n == 0) return record_ticket(D, ticket);
@@ -915,6 +925,7 @@ int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_
 }
 
 int b2_peer_pack(int dev, uint32_t dst_arena_id, const b2_span *spans, uint32_t n) {
+  Range r_("b2_peer_pack");
   DEV_OR_FAIL(D, dev);
   return move_spans_locked(D, spans, n, 0, dst_arena_id);
 }
