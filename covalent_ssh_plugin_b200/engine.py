@@ -448,9 +448,15 @@ class DeviceEngine:
         operands already live in the arena: dependents are released on the
         device through the MPMC queue, no host round trip per edge.  Returns the
         per-electron status words.  ``table`` has dtype _b2lib.TASK_DTYPE."""
+        return self.finish_dag(self.submit_dag(table, succ))
+
+    def submit_dag(self, table: np.ndarray, succ: Optional[np.ndarray] = None):
+        """Asynchronous half of ``run_dag``: returns a handle for ``finish_dag`` (so that
+        several GPUs can work on their part of one lattice level at the same time).  Only
+        one DAG per engine may be outstanding: its status words share a control region."""
         n = len(table)
         if n == 0:
-            return np.zeros(0, dtype=np.uint32)
+            return (0, 0)
         if n > self.queue_cap:
             raise ValueError(f"DAG of {n} electrons exceeds queue capacity {self.queue_cap}")
         self.flush()                       # keep launch order = submission order
@@ -464,9 +470,15 @@ class DeviceEngine:
         L.call("b2_enqueue", self.ordinal, table.ctypes.data, n, sp, ns, None)
         t = C.c_uint64()
         L.call("b2_launch", self.ordinal, self.ctrl_off, C.byref(t))
-        L.call("b2_wait", self.ordinal, t.value)
         self.counters["electrons"] += n
         self.counters["batches"] += 1
+        return (t.value, n)
+
+    def finish_dag(self, handle) -> np.ndarray:
+        ticket, n = handle
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        L.call("b2_wait", self.ordinal, ticket)
         return self._h_out[self.ctrl_off:self.ctrl_off + 4 * n].view(np.uint32).copy()
 
     # ------------------------------------------------------------- plumbing --

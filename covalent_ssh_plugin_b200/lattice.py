@@ -566,9 +566,12 @@ def _run_device_group(nodes, group: List[int], device, values, keep, res: Result
         for (dev, i), lv in lvl_of.items():
             levels.setdefault(lv, {}).setdefault(dev, []).append(i)
         for lv in sorted(levels):
-            for dev, idxs in levels[lv].items():
-                st = _launch(engines[dev], per_dev[dev], sorted(idxs))
-                _check(st, [per_dev[dev][i] for i in sorted(idxs)])
+            # every GPU works on its share of the level at the same time
+            handles = [(dev, sorted(idxs), _launch(engines[dev], per_dev[dev], sorted(idxs), wait=False))
+                       for dev, idxs in levels[lv].items()]
+            for dev, idxs, h in handles:
+                st = engines[dev].finish_dag(h)
+                _check(st, [per_dev[dev][i] for i in idxs])
                 res.stats["device_batches"] += 1
     res.stats["device_electrons"] += len(group)
     res.stats["device_tasks"] = res.stats.get("device_tasks", 0) + sum(len(v) for v in per_dev.values())
@@ -613,7 +616,7 @@ def _copy_fn_id() -> int:
     return _COPY_ID[0]
 
 
-def _launch(eng: DeviceEngine, recs: List[dict], subset: Optional[List[int]]) -> np.ndarray:
+def _launch(eng: DeviceEngine, recs: List[dict], subset: Optional[List[int]], wait: bool = True):
     """Task table for ``recs`` (all of them with on-device dependency release, or an
     independent ``subset`` of one level), ready electrons first."""
     if subset is None:
@@ -634,7 +637,7 @@ def _launch(eng: DeviceEngine, recs: List[dict], subset: Optional[List[int]]) ->
     for new, old in enumerate(subset):
         r = recs[old]
         table[new] = (r["fn_id"], r["flags"], r["arg0"], r["arg1"], r["out"], r["count"], r["nrows"], 0, 0, 0, 0)
-    return eng.run_dag(table, None)
+    return eng.run_dag(table, None) if wait else eng.submit_dag(table, None)
 
 
 def _check(st: np.ndarray, recs: Sequence[dict]) -> None:

@@ -20,7 +20,7 @@ def mk_executor(gpu_count, tmp_path_factory):
     from covalent_ssh_plugin_b200.engine import get_engine, shutdown_all
 
     shutdown_all()
-    for d in range(min(gpu_count, 2)):
+    for d in range(min(gpu_count, 8)):
         get_engine(d, arena_bytes=6 << 30, staging_bytes=256 << 20, n_segments=4, max_batch=1024)
     tmp = tmp_path_factory.mktemp("lat")
     key = tmp / "id_stub"
@@ -106,3 +106,22 @@ def test_diamond_across_two_gpus(mk_executor, gpu_count):
     assert r.status == ct.status.COMPLETED, r.error
     assert np.array_equal(r.result, host(x0, ws))
     assert "demoted" not in r.stats
+
+
+def test_diamond_1000_nodes_on_every_gpu(mk_executor, gpu_count):
+    """BASELINE config 4 as written: 1 000 nodes, 1 MiB operands, fan-out placed round-robin over
+    all GPUs of the box (7/8 of the edges cross GPUs at 8), reducer gathers the rows over NVLink."""
+    if gpu_count < 4:
+        pytest.skip("needs at least four GPUs")
+    from covalent_ssh_plugin_b200 import electrons as E, lattice as ct
+
+    g = min(gpu_count, 8)
+    exs = [mk_executor(f"cuda:{d}") for d in range(g)]
+    wf, host, x0, ws = diamond(ct, E, lambda i: exs[i % g], 998, 262144, seed=8)
+    t0 = time.perf_counter()
+    r = ct.get_result(ct.dispatch(wf)(x0, ws))
+    dt = time.perf_counter() - t0
+    assert r.status == ct.status.COMPLETED, r.error
+    assert np.array_equal(r.result, host(x0, ws))
+    assert "demoted" not in r.stats and r.stats["device_electrons"] == 1000
+    print(f"\n1000-node diamond over {g} GPUs: {dt * 1e3:.1f} ms end to end, {r.stats}")

@@ -17,9 +17,9 @@ SMALL = dict(arena_bytes=96 << 20, staging_bytes=16 << 20, n_segments=4, max_bat
 def gpu(tmp_path):
     engine_mod.shutdown_all()
     saved = _b2lib._lib
-    _b2lib._lib = FakeLib(n_devices=2)
-    engine_mod.get_engine(0, **SMALL)
-    engine_mod.get_engine(1, **SMALL)
+    _b2lib._lib = FakeLib(n_devices=4)
+    for d in range(4):
+        engine_mod.get_engine(d, **SMALL)
     key = tmp_path / "k"
     key.touch()
     mk = lambda host: SSHExecutor(username="u", hostname=host, ssh_key_file=str(key), cache_dir=str(tmp_path))  # noqa: E731
@@ -204,3 +204,16 @@ def test_put_many_get_many_chunking(gpu):
         assert b.shape == a.shape and b.flags.f_contiguous == a.flags.f_contiguous and np.array_equal(a, b)
         da.free()
     assert eng.heap.bytes_in_use() == 0
+
+
+def test_diamond_across_four_gpus(gpu):
+    """BASELINE config 4 shape: fan-out placed round-robin on every GPU, reducer on GPU 0 gathers
+    the rows of the other three over (modelled) peer arenas."""
+    exs = [gpu(f"cuda:{d}") for d in range(4)]
+    wf, host, x0, ws = _diamond(lambda i: exs[i % 4], 21, 2500, seed=11)
+    r = ct.get_result(ct.dispatch(wf)(x0, ws))
+    assert r.status == ct.status.COMPLETED, r.error
+    assert np.array_equal(r.result, host(x0, ws))
+    assert "demoted" not in r.stats and r.stats["device_electrons"] == 2 * 21 + 2
+    for d in range(4):
+        assert engine_mod.existing_engine(d).heap.bytes_in_use() == 0
