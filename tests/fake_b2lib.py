@@ -54,6 +54,7 @@ class FakeLib:
         self.err = b""
         self.delay_polls = delay_polls     # b2_poll answers NOTREADY this many times per ticket
         self.fail_init = fail_init         # first N b2_init calls fail (retry-path tests)
+        self.fail_launch = 0               # next N b2_launch calls fail (device lost mid-run)
         self._polls = {}
         self.calls = []
 
@@ -201,6 +202,11 @@ class FakeLib:
         return 0
 
     def b2_launch(self, dev, status_off, tref):
+        if self.fail_launch > 0:
+            self.fail_launch -= 1
+            d = self._dev(dev)
+            d.pending, d.pending_succ = [], []
+            return self._fail(L.B2_E_CUDA, "cudaLaunchKernel -> unspecified launch failure (injected)")
         d = self._dev(dev)
         tasks, succ = d.pending, d.pending_succ
         d.pending, d.pending_succ = [], []

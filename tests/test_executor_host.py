@@ -599,3 +599,22 @@ def test_large_elementwise_electrons_are_sliced(fake_lib, tmp_path):
     assert eng.counters["electrons"] - before >= 5            # task records, one per slice
     z = asyncio.run(ex.run(electrons.identity, [x], {}, {"dispatch_id": "big", "node_id": 1}))
     assert np.array_equal(z, x)
+
+
+def test_launch_failure_reaches_every_electron_of_the_batch(fake_lib, tmp_path):
+    """A CUDA failure while shipping a batch is raised from every run() of that batch (it is
+    not turned into a silent local run), the staging segments come back, and the engine keeps
+    working afterwards."""
+    eng = engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path, run_local_on_ssh_fail=True)     # must NOT mask a device failure
+    fake_lib.fail_launch = 1
+
+    async def go():
+        return await asyncio.gather(*[
+            ex.run(electrons.add_int, [i, 1], {}, {"dispatch_id": "boom", "node_id": i}) for i in range(10)],
+            return_exceptions=True)
+
+    out = asyncio.run(go())
+    assert all(isinstance(o, _b2lib.B2Error) for o in out)
+    assert sorted(eng._free_segments) == [0, 1, 2, 3] and sorted(eng._free_out) == [0, 1, 2, 3]
+    assert asyncio.run(ex.run(electrons.add_int, [2, 3], {}, {"dispatch_id": "after", "node_id": 0})) == 5
