@@ -94,19 +94,35 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
         if (use >= 1) mbar_wait(smem_addr(&empty_bar[s]), (use - 1) & 1u);
         return s;
       };
+      // The producer always holds one claimed ticket beyond the electron it is streaming,
+      // and — when that ticket lies in the ready prefix — its task record is already on its
+      // way into registers: the fetch-add and the record's L2 round trips overlap the tile
+      // issue of the current electron instead of sitting between two electrons.
+      uint32_t ticket = queue_claim(a.q);
+      b2_task t_next = {};
+      if (ticket < P) t_next = a.tasks[ticket];
       for (;;) {
-        const uint32_t ticket = queue_claim(a.q);
-        const uint32_t ti = (ticket < P) ? ticket : queue_take(a.q, ticket, a.n_tasks);
-        // a released dependent reads what other SMs just wrote with ordinary stores: order the
-        // acquire above before the copy engine's (async proxy) reads below
-        if (ticket >= P) asm volatile("fence.proxy.async.global;" ::: "memory");
+        const uint32_t cur = ticket;
+        uint32_t ti;
+        b2_task t;
+        if (cur < P) {
+          ti = cur;
+          t = t_next;
+        } else {
+          ti = queue_take(a.q, cur, a.n_tasks);
+          // a released dependent reads what other SMs just wrote with ordinary stores: order
+          // the acquire above before the copy engine's (async proxy) reads below
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          if (ti != kNoTask) t = a.tasks[ti];
+        }
         if (ti == kNoTask) {
           const uint32_t s = acquire();
           hdr[s].kind = kHdrExit;
           mbar_arrive(smem_addr(&full_bar[s]));
           break;
         }
-        const b2_task t = a.tasks[ti];
+        ticket = queue_claim(a.q);
+        if (ticket < P) t_next = a.tasks[ticket];
         uint32_t kind = B2_K__COUNT;
         FnEntry fn;
         fn.kind = 0; fn.alpha = 0.f; fn.beta = 0.f; fn.pad = 0; fn.ialpha = 0; fn.ibeta = 0;
