@@ -355,6 +355,19 @@ def run_cuda_arm(args, dist: Dist):
         kernels[name] = {"achieved_gbs": gbs, "frac": gbs / peak, "ms": ms,
                          "algorithmic_bytes_per_launch": 2.0 * total}
 
+    # CPU context for the pack figure: the same gather done by numpy on one host core (what the
+    # reference's transport would have to beat: it moves every payload byte through a file copy)
+    if dist.rank == 0:
+        host_src = np.frombuffer(np.random.default_rng(3).bytes(256 * MiB), dtype=np.uint8)
+        host_dst = np.empty(128 * MiB, dtype=np.uint8)
+        hp = np.random.default_rng(4).permutation(2048)
+        t0 = time.perf_counter()
+        for i, j in enumerate(hp):
+            host_dst[i * payload:(i + 1) * payload] = host_src[j * payload:(j + 1) * payload]
+        dt = time.perf_counter() - t0
+        kernels["pack"]["cpu_one_core_gbs"] = 2.0 * 2048 * payload / 1e9 / dt
+        del host_src, host_dst
+
     # ---- end to end through the executor ------------------------------------------
     tmp = tempfile.mkdtemp(prefix="b2-bench-")
     key = Path(tmp) / "id_stub"
