@@ -158,9 +158,12 @@ class Dist:
 
 
 # ------------------------------------------------------------- CPU baseline ---
-def cpu_baseline_sample(n_sample: int, payload: int, steps: int = 1, warmup: int = 0):
+def cpu_baseline_sample(n_sample: int, payload: int, steps: int = 1, warmup: int = 0, budget_s: float = 150.0):
     """Times the oracle port of the reference path (oracle/reference_port.py) on
-    n_sample electrons of the same workload, in waves of one coroutine per core."""
+    n_sample electrons of the same workload, in waves of one coroutine per core.  The whole
+    call is held to about ``budget_s`` seconds: if the first pass shows that warmup + steps
+    passes of n_sample electrons would take longer, later passes use a smaller sample (the
+    reference's cost per electron does not depend on the sample size)."""
     from covalent_ssh_plugin_b200 import electrons
     from oracle import reference_port as P
 
@@ -177,16 +180,23 @@ def cpu_baseline_sample(n_sample: int, payload: int, steps: int = 1, warmup: int
         # The baseline is timed in its best configuration.
         for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             s.env[var] = "1"
+        done = 0
+        n_now = n_sample
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            out = asyncio.run(P.run_many(s, calls, cores))
+            out = asyncio.run(P.run_many(s, calls[:n_now], cores))
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
+                done += n_now
+            left = warmup + steps - it - 1
+            if left and dt * left > budget_s:
+                n_now = max(min(cores, n_sample), int(n_now * budget_s / (dt * left)))
         assert np.array_equal(out[0], np.float32(2.0) * calls[0][1][0] + np.float32(1.0))
     dt = sum(times) / len(times)
+    n_sample = done / len(times)            # average sample per timed pass
     return {"value": n_sample / dt, "unit": "electrons/s", "cores": cores, "kind": "port",
-            "sample": f"{n_sample} electrons x {payload} B fp32 scale_add through oracle/reference_port.py "
+            "sample": f"{n_sample:.0f} electrons x {payload} B fp32 scale_add through oracle/reference_port.py "
                       f"(reference ssh.py+exec.py path, local transport), waves of {cores} coroutines, "
                       f"OMP/BLAS threads pinned to 1 per remote interpreter",
             "seconds": dt}, times
