@@ -28,6 +28,7 @@ Reference step (ssh.py)                      -> here
 from __future__ import annotations
 
 import asyncio
+import functools
 import os
 import socket
 import time
@@ -158,7 +159,7 @@ class _InFlight:
     """Book-keeping for one electron between the helper calls of ``run``; keyed
     by the same artefact names the reference uses as file names."""
 
-    __slots__ = ("encoded", "staged", "reason", "host_call", "host_result")
+    __slots__ = ("encoded", "staged", "reason", "host_call", "host_result", "rewrap")
 
     def __init__(self, encoded=None, reason: str = ""):
         self.encoded = encoded
@@ -166,6 +167,7 @@ class _InFlight:
         self.reason = reason
         self.host_call = None        # (fn, args, kwargs, workdir) when the opt-in host pool takes it
         self.host_result = None      # (result, exception) from the host pool
+        self.rewrap = None           # Covalent's TransportableObject class, when the call came wrapped in it
 
 
 # name (any of the five artefact names) -> _InFlight; process-wide like a cache dir
@@ -255,8 +257,14 @@ class SSHExecutor(RemoteExecutor):
         remote_script_file = f"{remote}exec_{operation_id}.py"
         remote_result_file = f"{remote}result_{operation_id}.pkl"
 
+        rewrap = None
+        if isinstance(fn, functools.partial):
+            unwrapped = _unwrap_covalent_call(fn, args, kwargs)
+            if unwrapped is not None:
+                fn, args, kwargs, rewrap = unwrapped
         try:
             entry = _InFlight(encoded=encode(fn, args, kwargs))
+            entry.rewrap = rewrap
         except NotDeviceEligible as why:
             entry = _InFlight(reason=str(why))
             if hostpool.enabled(get_config):      # opt-in: arbitrary Python runs in warm host workers
@@ -396,7 +404,10 @@ class SSHExecutor(RemoteExecutor):
         entry = _inflight[remote_result_file]
         if entry.host_result is not None:
             return entry.host_result
-        return conn.engine.result_of(entry.staged), None
+        result = conn.engine.result_of(entry.staged)
+        if entry.rewrap is not None:             # Covalent expects its wrapper's return type back
+            result = entry.rewrap(result)
+        return result, None
 
     async def cleanup(
         self,
@@ -483,6 +494,27 @@ class SSHExecutor(RemoteExecutor):
         conn.close()
         await conn.wait_closed()
         return result
+
+
+def _unwrap_covalent_call(fn, args, kwargs):
+    """Covalent core does not hand the user's function to ``run`` directly: it passes
+    ``functools.partial(wrapper_fn, TransportableObject(user_fn), call_before, call_after)``
+    with every argument wrapped in a TransportableObject, and expects a TransportableObject
+    back (covalent itself is not in /root/reference, so this is duck-typed on
+    ``get_deserialized()``).  Returns ``(user_fn, args, kwargs, TransportableObject)`` when the
+    call has exactly that shape and carries no call_before / call_after hooks, else None — the
+    partial then goes through untouched and, not being registered, takes the failure path."""
+    bound = fn.args
+    if fn.keywords or not bound or not hasattr(bound[0], "get_deserialized"):
+        return None
+    if any(bool(hook) for hook in bound[1:3]):      # DepsPip / DepsBash / DepsCall need a Python host
+        return None
+    wrapper_type = type(bound[0])
+
+    def plain(v):
+        return v.get_deserialized() if hasattr(v, "get_deserialized") else v
+
+    return (plain(bound[0]), [plain(a) for a in args], {k: plain(v) for k, v in kwargs.items()}, wrapper_type)
 
 
 def _emit_artifacts(function_file, script_file, result_file, fn, args, kwargs, result, exception) -> None:

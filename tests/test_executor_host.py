@@ -618,3 +618,48 @@ def test_launch_failure_reaches_every_electron_of_the_batch(fake_lib, tmp_path):
     assert all(isinstance(o, _b2lib.B2Error) for o in out)
     assert sorted(eng._free_segments) == [0, 1, 2, 3] and sorted(eng._free_out) == [0, 1, 2, 3]
     assert asyncio.run(ex.run(electrons.add_int, [2, 3], {}, {"dispatch_id": "after", "node_id": 0})) == 5
+
+
+# ------------------------------------------------------- calls as Covalent core makes them ---
+class FakeTransportable:
+    """Duck-type of covalent's TransportableObject (serialises on construction)."""
+
+    def __init__(self, obj):
+        import cloudpickle
+
+        self._blob = cloudpickle.dumps(obj)
+
+    def get_deserialized(self):
+        import cloudpickle
+
+        return cloudpickle.loads(self._blob)
+
+
+def _covalent_wrapper(user_fn, call_before, call_after, *args, **kwargs):
+    fn = user_fn.get_deserialized()
+    out = fn(*[a.get_deserialized() for a in args], **{k: v.get_deserialized() for k, v in kwargs.items()})
+    return FakeTransportable(out)
+
+
+def test_covalent_style_wrapped_call_runs_on_the_device(fake_lib, tmp_path):
+    """functools.partial(wrapper, TransportableObject(fn), [], []) with TransportableObject
+    arguments (how Covalent core calls run) is unwrapped, runs on the device, and the result
+    comes back wrapped the same way."""
+    import functools
+
+    eng = engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path)
+    x = np.arange(300, dtype=np.float32)
+    call = functools.partial(_covalent_wrapper, FakeTransportable(electrons.scale_add), [], [])
+    before = eng.counters["electrons"]
+    out = asyncio.run(ex.run(call, [FakeTransportable(x)], {}, {"dispatch_id": "cov", "node_id": 0}))
+    assert isinstance(out, FakeTransportable)
+    assert np.array_equal(out.get_deserialized(), np.float32(2.0) * x + np.float32(1.0))
+    assert eng.counters["electrons"] == before + 1
+    # with call_before hooks the electron needs a Python host: failure path (or local run if opted in)
+    hooked = functools.partial(_covalent_wrapper, FakeTransportable(electrons.scale_add), ["pip install x"], [])
+    with pytest.raises(RuntimeError):
+        asyncio.run(ex.run(hooked, [FakeTransportable(x)], {}, {"dispatch_id": "cov", "node_id": 1}))
+    ex.run_local_on_ssh_fail = True
+    out = asyncio.run(ex.run(hooked, [FakeTransportable(x)], {}, {"dispatch_id": "cov", "node_id": 2}))
+    assert np.array_equal(out.get_deserialized(), np.float32(2.0) * x + np.float32(1.0))
