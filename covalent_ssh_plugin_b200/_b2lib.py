@@ -17,16 +17,17 @@ LIB_PATH = PKG_DIR / "libb2exec.so"
 B2_OK = 0
 B2_E_CUDA, B2_E_ARG, B2_E_STATE, B2_E_NOMEM, B2_E_NOTREADY, B2_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
-TS_PENDING, TS_OK, TS_OVERFLOW, TS_BAD_FN, TS_BAD_ARG = 0, 1, 2, 3, 4
+TS_PENDING, TS_OK, TS_OVERFLOW, TS_BAD_FN, TS_BAD_ARG, TS_CANCELLED = 0, 1, 2, 3, 4, 5
 
 K_NONE, K_COPY, K_SCALE_ADD, K_ADD, K_MUL, K_AXPY, K_SUM, K_STACK_SUM, K_IADD, K_IMUL, K_ISCALE_ADD = range(11)
 
-F_IMM0, F_IMM1 = 0x1, 0x2
+F_IMM0, F_IMM1, F_CANCELLED = 0x1, 0x2, 0x4
+BATCH_INDEPENDENT = 0x1
 F_ARENA0_SHIFT, F_ARENA1_SHIFT, F_ARENAO_SHIFT = 8, 12, 16
 NO_STATUS_COPY = 0xFFFFFFFFFFFFFFFF
 MAX_FN = 1024
 MAX_ARENAS = 9
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class B2Error(RuntimeError):
@@ -66,6 +67,32 @@ class Span(C.Structure):
     _fields_ = [("src_off", C.c_uint64), ("dst_off", C.c_uint64), ("bytes", C.c_uint64)]
 
 
+class CopyJob(C.Structure):
+    """struct b2_copy_job (24 bytes)."""
+
+    _fields_ = [("src", C.c_uint64), ("dst_off", C.c_uint64), ("bytes", C.c_uint64)]
+
+
+class Batch(C.Structure):
+    """struct b2_batch: one whole batch for b2_submit."""
+
+    _fields_ = [
+        ("jobs", C.c_void_p),
+        ("tasks", C.c_void_p),
+        ("n_jobs", C.c_uint32),
+        ("n_tasks", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("in_off", C.c_uint64),
+        ("in_bytes", C.c_uint64),
+        ("status_host_off", C.c_uint64),
+        ("out_dev_off", C.c_uint64),
+        ("out_host_off", C.c_uint64),
+        ("out_bytes", C.c_uint64),
+        ("ticket", C.c_uint64),
+    ]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("cc_major", C.c_int32),
@@ -94,7 +121,7 @@ class Stats(C.Structure):
     ]
 
 
-assert C.sizeof(Task) == 64 and C.sizeof(Span) == 24
+assert C.sizeof(Task) == 64 and C.sizeof(Span) == 24 and C.sizeof(CopyJob) == 24 and C.sizeof(Batch) == 88
 
 # numpy dtypes with the same layouts (vectorised table building)
 TASK_DTYPE = [
@@ -103,6 +130,7 @@ TASK_DTYPE = [
     ("succ_count", "<u4"), ("tag", "<u8"),
 ]
 SPAN_DTYPE = [("src_off", "<u8"), ("dst_off", "<u8"), ("bytes", "<u8")]
+JOB_DTYPE = [("src", "<u8"), ("dst_off", "<u8"), ("bytes", "<u8")]
 
 _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
@@ -111,6 +139,7 @@ _u64p = C.POINTER(C.c_uint64)
 _SIGNATURES = {
     "b2_last_error": ([], False),
     "b2_abi_version": ([], False),
+    "b2_source_hash": ([], False),
     "b2_device_count": ([C.POINTER(C.c_int)], True),
     "b2_init": ([C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32], True),
     "b2_shutdown": ([C.c_int], True),
@@ -131,6 +160,9 @@ _SIGNATURES = {
     "b2_register": ([C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64], True),
     "b2_enqueue": ([C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _u32p], True),
     "b2_launch": ([C.c_int, C.c_uint64, _u64p], True),
+    "b2_submit": ([C.c_int, C.POINTER(Batch)], True),
+    "b2_stage_copy": ([C.c_int, C.c_void_p, C.c_uint32], True),
+    "b2_cancel": ([C.c_int, C.c_uint64, C.c_uint32, C.c_uint32], True),
     "b2_mark": ([C.c_int, _u64p], True),
     "b2_poll": ([C.c_int, C.c_uint64], False),
     "b2_wait": ([C.c_int, C.c_uint64], True),
@@ -166,16 +198,24 @@ def load():
             f"{path} not found: build it with `python -m covalent_ssh_plugin_b200.build` "
             "(there is no CPU implementation to fall back to)"
         )
-    lib = C.CDLL(str(path))
+    try:
+        lib = C.CDLL(str(path))
+    except OSError as err:          # never let the connect-retry loop treat this as "host unreachable"
+        raise LibraryMissing(f"{path} could not be loaded: {err}") from err
     for name, (argtypes, _) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "b2_last_error" else C.c_int
+        fn.restype = C.c_char_p if name in ("b2_last_error", "b2_source_hash") else C.c_int
     got = lib.b2_abi_version()
     if got != ABI_VERSION:
         raise RuntimeError(f"libb2exec ABI version {got} != binding version {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def source_hash() -> str:
+    """Which source tree the loaded library was built from (build.py fingerprint, 16 hex digits)."""
+    return (load().b2_source_hash() or b"").decode("ascii", "replace")
 
 
 def last_error() -> str:

@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import logging
 import os
-import tomllib
 from pathlib import Path
 from typing import Any
 
@@ -46,6 +45,10 @@ def _config() -> dict:
         path = Path(cfg_dir) / "covalent.conf"
         data = {}
         if path.is_file():
+            try:
+                import tomllib             # Python >= 3.11
+            except ImportError:            # 3.9 / 3.10 (pyproject: requires-python >= 3.9)
+                import tomli as tomllib
             with open(path, "rb") as fh:
                 data = tomllib.load(fh)
         _loaded = data

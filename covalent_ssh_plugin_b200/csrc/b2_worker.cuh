@@ -192,7 +192,7 @@ __device__ uint32_t cb_axpy(const Ctx &c) {
 
 // out[0] = sum(x): per-thread double partials, shuffle tree, one fp32 rounding.
 // Order differs from numpy's pairwise float32 sum; the result is at least as
-// accurate (parity bar: 1e-6 relative, tests/test_parity_gpu.py).
+// accurate (parity bar: 1e-6 relative, tests/test_kernels_gpu.py).
 __device__ uint32_t cb_sum(const Ctx &c) {
   if (!c.a0 || !aligned16(c.a0)) return B2_TS_BAD_ARG;
   __shared__ double warp_part[kWorkerThreads / kWarp];
@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
       if (ti == kNoTask) break;
       const uint32_t kind = sl.kind;
       uint32_t status;
-      if (kind >= B2_K__COUNT) {
+      if (sl.t.flags & B2_F_CANCELLED) {
+        status = B2_TS_CANCELLED;   // tombstone (b2_cancel): successors are still released below
+      } else if (kind >= B2_K__COUNT) {
         status = B2_TS_BAD_FN;
       } else {
         Ctx c;

@@ -131,6 +131,20 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
           kind = fn.kind;
           if (kind >= B2_K__COUNT || (kind == B2_K_NONE && t.fn_id != 0)) kind = B2_K__COUNT;
         }
+        if (t.flags & B2_F_CANCELLED) {
+          // tombstone (b2_cancel): nothing runs, the status says so, successors are still released
+          const uint32_t s = acquire();
+          StageHdr &h = hdr[s];
+          h.kind = kHdrFailed;
+          h.status = B2_TS_CANCELLED;
+          h.task = ti;
+          h.last = 1;
+          h.succ_begin = t.succ_begin;
+          h.succ_count = t.succ_count;
+          mbar_arrive(smem_addr(&full_bar[s]));
+          ++it;
+          continue;
+        }
         if (kind == B2_K__COUNT || !is_streaming_kind(kind)) {
           // one stage carries the whole electron: bad fn_id, or a callback that reads global
           // memory itself (SUM, STACK_SUM, integer electrons, the gate)

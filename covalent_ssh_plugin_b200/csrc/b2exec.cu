@@ -16,13 +16,18 @@
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "b2_hostcopy.h"
 #include "b2_spans.cuh"
 #include "b2_spans_tma.cuh"
 #include "b2_worker.cuh"
@@ -52,10 +57,25 @@ int fail(int code, const char *fmt, ...) {
                   __LINE__);                                                                  \
   } while (0)
 
+#ifndef B2_SRC_HASH
+#define B2_SRC_HASH "unknown"
+#endif
+
 constexpr int kMaxDevices = 16;
-constexpr int kRing = 4;          // staging ring depth
+constexpr int kRing = 8;          // staging ring depth
 constexpr int kTickets = 4096;    // completion events kept alive
 constexpr int kMaxUserEvents = 256;
+constexpr size_t kCopyPieceBytes = 256 * 1024;   // large operands are split across the copy threads
+
+// One queued b2_submit (the caller keeps jobs / tasks alive until the ticket completes).
+struct Submission {
+  b2_batch b;
+  uint64_t ticket = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> cancels;   // tombstones that arrived while it was queued
+};
+
+// Where the batch behind a ticket is, for b2_cancel.
+enum TicketPhase : uint8_t { kPhaseNone = 0, kPhaseQueued = 1, kPhaseTabled = 2, kPhaseLaunched = 3 };
 
 // A pinned host buffer with a device mirror, guarded by an event so it is not
 // rewritten while an earlier async copy may still be reading it.
@@ -115,8 +135,24 @@ struct Device {
 
   cudaEvent_t tickets[kTickets] = {};
   uint64_t next_ticket = 1;
+  // per ticket slot (index = ticket % kTickets), guarded by mu
+  bool ticket_recorded[kTickets] = {};     // its event has been recorded (async tickets are recorded late)
+  int ticket_err[kTickets] = {};           // failure of the asynchronous pipeline, reported by poll / wait
+  std::string ticket_msg[kTickets];
+  uint8_t ticket_phase[kTickets] = {};
+  int8_t ticket_slot[kTickets] = {};       // task-ring slot holding the batch's table (-1: none)
+  uint32_t ticket_ntasks[kTickets] = {};
+  std::condition_variable ticket_cv;       // signalled when an async ticket gets recorded
   cudaEvent_t user_ev[kMaxUserEvents] = {};
   uint32_t n_user_ev = 0;
+
+  // asynchronous submissions (b2_submit): one thread per device issues them in order
+  std::thread submitter;
+  std::mutex qmu;
+  std::condition_variable qcv, qidle;
+  std::deque<Submission> queue;
+  bool q_busy = false, q_stop = false;
+  Submission *q_current = nullptr;   // the one the submission thread is working on
 
   b2_stats stats = {};
 };
@@ -131,6 +167,21 @@ Device *get(int dev) {
 #define DEV_OR_FAIL(D, dev)                                              \
   Device *D = get(dev);                                                  \
   if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);  \
+  std::lock_guard<std::mutex> lock_(D->mu);                              \
+  if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev); \
+  CU(cudaSetDevice(dev))
+
+// Calls whose effect is ordered against queued b2_submit batches first wait until the
+// submission thread has issued everything queued so far (program order is kept).
+void drain_submissions(Device *D) {
+  std::unique_lock<std::mutex> lk(D->qmu);
+  D->qidle.wait(lk, [&] { return D->queue.empty() && !D->q_busy; });
+}
+
+#define DEV_ORDERED(D, dev)                                              \
+  Device *D = get(dev);                                                  \
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);  \
+  if (std::this_thread::get_id() != D->submitter.get_id()) drain_submissions(D); \
   std::lock_guard<std::mutex> lock_(D->mu);                              \
   if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev); \
   CU(cudaSetDevice(dev))
@@ -286,8 +337,11 @@ int env_int(const char *name, int dflt) {
 // =============================================================== C ABI =====
 extern "C" {
 
+static void submit_loop(Device *D);
+
 const char *b2_last_error(void) { return g_err.c_str(); }
 int b2_abi_version(void) { return (int)B2_ABI_VERSION; }
+const char *b2_source_hash(void) { return B2_SRC_HASH; }
 
 int b2_device_count(int *count) {
   if (!count) return fail(B2_E_ARG, "count is NULL");
@@ -429,6 +483,21 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   // fn_id 0 stays kind NONE: the gate electron, a registered no-op used to fan
   // one dependency out to many successors.
   CU(cudaStreamSynchronize(D->stream));
+  for (int i = 0; i < kTickets; ++i) {
+    D->ticket_recorded[i] = false;
+    D->ticket_err[i] = 0;
+    D->ticket_phase[i] = kPhaseNone;
+    D->ticket_slot[i] = -1;
+    D->ticket_ntasks[i] = 0;
+  }
+  {
+    std::lock_guard<std::mutex> ql(D->qmu);
+    D->queue.clear();
+    D->q_busy = false;
+    D->q_stop = false;
+    D->q_current = nullptr;
+  }
+  D->submitter = std::thread(submit_loop, D);
   D->up = true;
   return B2_OK;
 }
@@ -436,6 +505,18 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
 int b2_shutdown(int dev) {
   Device *D = get(dev);
   if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    if (!D->up) return fail(B2_E_STATE, "device %d is not initialised", dev);
+  }
+  // queued submissions are issued, then the submission thread leaves (it needs the device
+  // lock to finish, so this happens before we take it)
+  {
+    std::lock_guard<std::mutex> ql(D->qmu);
+    D->q_stop = true;
+  }
+  D->qcv.notify_all();
+  if (D->submitter.joinable()) D->submitter.join();
   std::lock_guard<std::mutex> lock_(D->mu);
   if (!D->up) return fail(B2_E_STATE, "device %d is not initialised", dev);
   cudaSetDevice(dev);
@@ -469,6 +550,7 @@ int b2_shutdown(int dev) {
   D->h_in_bytes = D->h_out_bytes = 0;
   D->n_arenas = 0;
   D->up = false;
+  D->ticket_cv.notify_all();
   return B2_OK;
 }
 
@@ -525,7 +607,7 @@ int b2_arena_base(int dev, uint32_t arena_id, void **ptr, uint64_t *bytes) {
 }
 
 int b2_detach_host_buffer(int dev, int which) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (which == 0) {
     D->h_in = nullptr;
     D->h_in_bytes = 0;
@@ -539,7 +621,7 @@ int b2_detach_host_buffer(int dev, int which) {
 }
 
 int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (host_off + bytes > D->h_in_bytes || host_off + bytes < host_off)
     return fail(B2_E_ARG, "h2d: host range [%llu, +%llu) outside ingress staging (%llu bytes)",
                 (unsigned long long)host_off, (unsigned long long)bytes,
@@ -554,7 +636,7 @@ int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes) {
 }
 
 int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (host_off + bytes > D->h_out_bytes || host_off + bytes < host_off)
     return fail(B2_E_ARG, "d2h: host range [%llu, +%llu) outside egress staging (%llu bytes)",
                 (unsigned long long)host_off, (unsigned long long)bytes,
@@ -572,7 +654,7 @@ int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes) {
 }
 
 int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (!src && bytes) return fail(B2_E_ARG, "src is NULL");
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "write: device range outside arena");
@@ -583,7 +665,7 @@ int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes) {
 }
 
 int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (!dst && bytes) return fail(B2_E_ARG, "dst is NULL");
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "read: device range outside arena");
@@ -594,7 +676,7 @@ int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes) {
 }
 
 int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "fill: device range outside arena");
   if (!bytes) return B2_OK;
@@ -605,7 +687,7 @@ int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
 // ----------------------------------------------------------- pack / unpack --
 int b2_move_spans(int dev, const b2_span *spans, uint32_t n) {
   Range r_("b2_move_spans");
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   return move_spans_locked(D, spans, n, 0, 0);
 }
 
@@ -615,7 +697,7 @@ static int pack_like(int dev, bool gather, const uint64_t *scattered, const uint
   if (n && (!scattered || !sizes)) return fail(B2_E_ARG, "offsets/sizes is NULL");
   if (align == 0 || (align & (align - 1))) return fail(B2_E_ARG, "align must be a power of two");
   Range r_(gather ? "b2_pack" : "b2_unpack");
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   std::vector<b2_span> spans(n);
   uint64_t cur = run_off;
   for (uint32_t i = 0; i < n; ++i) {
@@ -647,7 +729,7 @@ int b2_unpack(int dev, uint64_t src_off, const uint64_t *dst_offs, const uint64_
 // -------------------------------------------------- callback table + queue --
 int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta, int64_t ialpha,
                 int64_t ibeta) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (fn_id >= B2_MAX_FN) return fail(B2_E_ARG, "fn_id %u >= B2_MAX_FN", fn_id);
   if (kind < 0 || kind >= B2_K__COUNT) return fail(B2_E_ARG, "unknown callback kind %d", kind);
   if (fn_id == 0 && kind != B2_K_NONE)
@@ -666,9 +748,12 @@ int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta, in
   return B2_OK;
 }
 
-int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
-               uint32_t *first_index) {
-  DEV_OR_FAIL(D, dev);
+// Appends n task records to the pending batch in the current ring slot.  One pass over the
+// table: each record is copied and fixed up (successor range made batch-relative, dependency
+// count biased) in the same loop that tracks the ready prefix; a batch the caller declares
+// independent (plain fan-out) is a straight memcpy.  Caller holds the device lock.
+static int enqueue_locked(Device *D, const b2_task *tasks, uint32_t n, const uint32_t *succ,
+                          uint32_t n_succ, uint32_t *first_index, bool independent) {
   if (n && !tasks) return fail(B2_E_ARG, "tasks is NULL");
   if (n_succ && !succ) return fail(B2_E_ARG, "succ is NULL but n_succ = %u", n_succ);
   if ((uint64_t)D->pend_tasks + n > D->qcap)
@@ -685,25 +770,31 @@ int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, 
   }
   if (first_index) *first_index = D->pend_tasks;
   b2_task *ht = reinterpret_cast<b2_task *>(s.h) + D->pend_tasks;
-  memcpy(ht, tasks, (size_t)n * sizeof(b2_task));
-  // successor ranges are given relative to this call's succ array
-  for (uint32_t i = 0; i < n; ++i) {
-    if (ht[i].succ_count) {
-      if ((uint64_t)ht[i].succ_begin + ht[i].succ_count > n_succ)
-        return fail(B2_E_ARG, "task %u: successor range [%u, +%u) outside succ[%u]", i,
-                    ht[i].succ_begin, ht[i].succ_count, n_succ);
-      ht[i].succ_begin += D->pend_succ;
+  if (independent) {
+    memcpy(ht, tasks, (size_t)n * sizeof(b2_task));
+    if (D->pend_prefix_open) D->pend_prefix += n;
+  } else {
+    bool open = D->pend_prefix_open;
+    uint32_t prefix = D->pend_prefix;
+    for (uint32_t i = 0; i < n; ++i) {
+      b2_task t = tasks[i];
+      if (t.succ_count) {
+        if ((uint64_t)t.succ_begin + t.succ_count > n_succ)
+          return fail(B2_E_ARG, "task %u: successor range [%u, +%u) outside succ[%u]", i,
+                      t.succ_begin, t.succ_count, n_succ);
+        t.succ_begin += D->pend_succ;   // ranges are given relative to this call's succ array
+      }
+      if (t.deps) {
+        if (t.deps >= kDepBias) return fail(B2_E_ARG, "task %u: deps too large", i);
+        t.deps += kDepBias;  // see kDepBias in b2_device.cuh
+        open = false;
+      } else if (open) {
+        ++prefix;
+      }
+      ht[i] = t;
     }
-    if (ht[i].deps) {
-      if (ht[i].deps >= kDepBias) return fail(B2_E_ARG, "task %u: deps too large", i);
-      ht[i].deps += kDepBias;  // see kDepBias in b2_device.cuh
-    }
-  }
-  for (uint32_t i = 0; i < n && D->pend_prefix_open; ++i) {
-    if (ht[i].deps == 0)
-      D->pend_prefix += 1;
-    else
-      D->pend_prefix_open = false;
+    D->pend_prefix_open = open;
+    D->pend_prefix = prefix;
   }
   if (n_succ)
     memcpy(reinterpret_cast<uint32_t *>(s.h + succ_off) + D->pend_succ, succ, (size_t)n_succ * 4);
@@ -712,9 +803,30 @@ int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, 
   return B2_OK;
 }
 
-static int record_ticket(Device *D, uint64_t *ticket) {
+int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
+               uint32_t *first_index) {
+  DEV_ORDERED(D, dev);
+  return enqueue_locked(D, tasks, n, succ, n_succ, first_index, false);
+}
+
+// ---- tickets ---------------------------------------------------------------
+// A ticket is a sequence number; slot ticket % kTickets holds its event and state.
+static uint64_t alloc_ticket(Device *D, TicketPhase phase) {
   const uint64_t t = D->next_ticket++;
-  cudaEvent_t &ev = D->tickets[t % kTickets];
+  const int i = (int)(t % kTickets);
+  D->ticket_recorded[i] = false;
+  D->ticket_err[i] = 0;
+  D->ticket_phase[i] = phase;
+  D->ticket_slot[i] = -1;
+  D->ticket_ntasks[i] = 0;
+  return t;
+}
+
+// Records ticket t's event after everything issued so far (compute stream and, if copies are
+// queued there, the egress stream).
+static int record_ticket_event(Device *D, uint64_t t) {
+  const int i = (int)(t % kTickets);
+  cudaEvent_t &ev = D->tickets[i];
   if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (D->egress_dirty) {
     // the ticket covers the compute stream AND the copies queued on the egress stream
@@ -725,15 +837,24 @@ static int record_ticket(Device *D, uint64_t *ticket) {
   } else {
     CU(cudaEventRecord(ev, D->stream));
   }
+  D->ticket_recorded[i] = true;
+  return B2_OK;
+}
+
+static int record_ticket(Device *D, uint64_t *ticket) {
+  const uint64_t t = alloc_ticket(D, kPhaseNone);
+  int rc = record_ticket_event(D, t);
+  if (rc) return rc;
   if (ticket) *ticket = t;
   return B2_OK;
 }
 
-int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
-  Range r_("b2_launch");
-  DEV_OR_FAIL(D, dev);
+// Uploads the pending batch's table, launches the worker over it and queues the status copy.
+// `t` (0 = none) is the ticket that will cover this launch: its slot is remembered for
+// b2_cancel.  Caller holds the device lock and records the ticket afterwards.
+static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   const uint32_t n = D->pend_tasks;
-  if (n == 0) return record_ticket(D, ticket);
+  if (n == 0) return B2_OK;
   if (status_host_off != UINT64_MAX &&
       (status_host_off + (uint64_t)n * 4 > D->h_out_bytes || (status_host_off & 3)))
     return fail(B2_E_ARG, "status_host_off %llu (+%u words) outside egress staging",
@@ -796,24 +917,66 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
     D->stats.bytes_d2h += (uint64_t)n * 4;
   }
   D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
+  if (t) {
+    const int ti = (int)(t % kTickets);
+    D->ticket_slot[ti] = (int8_t)D->task_slot;
+    D->ticket_ntasks[ti] = n;
+    D->ticket_phase[ti] = kPhaseLaunched;
+  }
   D->task_slot = (D->task_slot + 1) % kRing;
   D->pend_tasks = D->pend_succ = 0;
   D->pend_prefix = 0;
   D->pend_prefix_open = true;
-  return record_ticket(D, ticket);
+  return B2_OK;
+}
+
+int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
+  Range r_("b2_launch");
+  DEV_ORDERED(D, dev);
+  const uint64_t t = alloc_ticket(D, kPhaseNone);
+  int rc = launch_locked(D, status_host_off, t);
+  if (rc == B2_OK) rc = record_ticket_event(D, t);
+  if (rc) {
+    // the ticket exists but will never complete normally: make poll / wait report the failure
+    const int i = (int)(t % kTickets);
+    D->ticket_err[i] = rc;
+    D->ticket_msg[i] = g_err;
+    D->ticket_recorded[i] = true;
+    D->pend_tasks = D->pend_succ = 0;
+    D->pend_prefix = 0;
+    D->pend_prefix_open = true;
+    return rc;
+  }
+  if (ticket) *ticket = t;
+  return B2_OK;
 }
 
 int b2_mark(int dev, uint64_t *ticket) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   return record_ticket(D, ticket);
+}
+
+// Ticket state for poll / wait.  Returns B2_OK when its event may be queried (copied to *ev),
+// 1 when the ticket is so old that it has certainly completed, B2_E_NOTREADY when the
+// submission thread has not recorded it yet, or the pipeline's error.
+static int ticket_lookup(Device *D, uint64_t ticket, cudaEvent_t *ev) {
+  if (ticket == 0 || ticket >= D->next_ticket)
+    return fail(B2_E_ARG, "unknown ticket %llu", (unsigned long long)ticket);
+  if (D->next_ticket - ticket >= (uint64_t)kTickets) return 1;  // event slot recycled: long done
+  const int i = (int)(ticket % kTickets);
+  if (!D->ticket_recorded[i]) return B2_E_NOTREADY;
+  if (D->ticket_err[i]) return fail(D->ticket_err[i], "%s", D->ticket_msg[i].c_str());
+  *ev = D->tickets[i];
+  return B2_OK;
 }
 
 int b2_poll(int dev, uint64_t ticket) {
   DEV_OR_FAIL(D, dev);
-  if (ticket == 0 || ticket >= D->next_ticket) return fail(B2_E_ARG, "unknown ticket %llu",
-                                                           (unsigned long long)ticket);
-  if (D->next_ticket - ticket >= (uint64_t)kTickets) return B2_OK;  // event slot recycled: long done
-  cudaError_t e = cudaEventQuery(D->tickets[ticket % kTickets]);
+  cudaEvent_t ev = nullptr;
+  const int rc = ticket_lookup(D, ticket, &ev);
+  if (rc == 1) return B2_OK;
+  if (rc != B2_OK) return rc;
+  cudaError_t e = cudaEventQuery(ev);
   if (e == cudaSuccess) return B2_OK;
   if (e == cudaErrorNotReady) return B2_E_NOTREADY;
   return fail(B2_E_CUDA, "cudaEventQuery -> %s", cudaGetErrorString(e));
@@ -822,11 +985,20 @@ int b2_poll(int dev, uint64_t ticket) {
 int b2_wait(int dev, uint64_t ticket) {
   cudaEvent_t ev = nullptr;
   {
-    DEV_OR_FAIL(D, dev);
-    if (ticket == 0 || ticket >= D->next_ticket)
-      return fail(B2_E_ARG, "unknown ticket %llu", (unsigned long long)ticket);
-    if (D->next_ticket - ticket >= (uint64_t)kTickets) return B2_OK;
-    ev = D->tickets[ticket % kTickets];
+    Device *D = get(dev);
+    if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+    std::unique_lock<std::mutex> lk(D->mu);
+    if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev);
+    int rc;
+    for (;;) {
+      rc = ticket_lookup(D, ticket, &ev);
+      if (rc != B2_E_NOTREADY) break;
+      D->ticket_cv.wait(lk);          // an asynchronous ticket: wait until it has been issued
+      if (!D->up) return fail(B2_E_STATE, "device %d was shut down while waiting", dev);
+    }
+    if (rc == 1) return B2_OK;
+    if (rc != B2_OK) return rc;
+    CU(cudaSetDevice(dev));
   }
   // Block outside the device lock so other threads can keep submitting.
   CU(cudaEventSynchronize(ev));
@@ -836,7 +1008,7 @@ int b2_wait(int dev, uint64_t ticket) {
 int b2_sync(int dev) {
   cudaStream_t st, up, eg;
   {
-    DEV_OR_FAIL(D, dev);
+    DEV_ORDERED(D, dev);
     st = D->stream;
     up = D->upload;
     eg = D->egress;
@@ -845,6 +1017,233 @@ int b2_sync(int dev) {
   CU(cudaStreamSynchronize(st));
   CU(cudaStreamSynchronize(eg));
   return B2_OK;
+}
+
+// ------------------------------------------------- asynchronous submissions --
+// Splits copy jobs into pieces for the host copy pool.
+static int run_copy_jobs(Device *D, const b2_copy_job *jobs, uint32_t n) {
+  if (n == 0) return B2_OK;
+  if (!jobs) return fail(B2_E_ARG, "jobs is NULL");
+  std::vector<b2host::CopyPiece> pieces;
+  pieces.reserve(n);
+  uint8_t *base;
+  uint64_t cap;
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    base = D->h_in;
+    cap = D->h_in_bytes;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    const b2_copy_job &j = jobs[i];
+    if (j.bytes == 0) continue;
+    if (!j.src) return fail(B2_E_ARG, "copy job %u: src is NULL", i);
+    if (j.dst_off + j.bytes > cap || j.dst_off + j.bytes < j.dst_off)
+      return fail(B2_E_ARG, "copy job %u: [%llu, +%llu) outside ingress staging (%llu bytes)", i,
+                  (unsigned long long)j.dst_off, (unsigned long long)j.bytes, (unsigned long long)cap);
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(static_cast<uintptr_t>(j.src));
+    for (uint64_t off = 0; off < j.bytes; off += kCopyPieceBytes)
+      pieces.push_back({src + off, base + j.dst_off + off,
+                        (size_t)std::min<uint64_t>(kCopyPieceBytes, j.bytes - off)});
+  }
+  b2host::copy_pieces(pieces.data(), pieces.size());
+  return B2_OK;
+}
+
+int b2_stage_copy(int dev, const b2_copy_job *jobs, uint32_t n) {
+  Device *D = get(dev);
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev);
+  }
+  return run_copy_jobs(D, jobs, n);
+}
+
+// Sets B2_F_CANCELLED on records [first, first+count) of the table in ring slot `slot`;
+// when the table is already on the device the flag words are re-uploaded (4 bytes each,
+// from the pinned host copy, on the upload stream — not behind the running kernel).
+static int tombstone_locked(Device *D, int slot, uint32_t n_tasks, uint32_t first, uint32_t count,
+                            bool on_device) {
+  if (slot < 0 || first >= n_tasks) return B2_OK;
+  Staging &s = D->task_ring[slot];
+  b2_task *ht = reinterpret_cast<b2_task *>(s.h);
+  const uint32_t end = (uint32_t)std::min<uint64_t>((uint64_t)first + count, n_tasks);
+  for (uint32_t i = first; i < end; ++i) ht[i].flags |= B2_F_CANCELLED;
+  if (on_device) {
+    for (uint32_t i = first; i < end; ++i) {
+      const size_t off = (size_t)i * sizeof(b2_task) + offsetof(b2_task, flags);
+      CU(cudaMemcpyAsync(s.d + off, s.h + off, 4, cudaMemcpyHostToDevice, D->upload));
+    }
+  }
+  return B2_OK;
+}
+
+// The per-device submission thread: issues queued batches in order.
+static void submit_fail(Device *D, uint64_t t, int rc) {
+  const int i = (int)(t % kTickets);
+  D->ticket_err[i] = rc ? rc : B2_E_CUDA;
+  D->ticket_msg[i] = g_err;
+  D->ticket_recorded[i] = true;
+  D->pend_tasks = D->pend_succ = 0;
+  D->pend_prefix = 0;
+  D->pend_prefix_open = true;
+}
+
+static void submit_one(Device *D, Submission &sub) {
+  const b2_batch &b = sub.b;
+  const uint64_t t = sub.ticket;
+  const int ti = (int)(t % kTickets);
+  int rc = B2_OK;
+  // 1. make sure the ring slot is free WITHOUT holding the device lock (poll / wait stay responsive)
+  {
+    cudaEvent_t wait_ev = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(D->mu);
+      Staging &s = D->task_ring[D->task_slot];
+      if (s.in_flight) wait_ev = s.ev;
+    }
+    if (wait_ev) {
+      cudaSetDevice(D->dev);
+      cudaEventSynchronize(wait_ev);
+    }
+  }
+  // 2. table into the ring slot (tombstones that arrived while queued are applied to it)
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    cudaSetDevice(D->dev);
+    if (D->pend_tasks != 0) {
+      rc = fail(B2_E_STATE, "b2_submit while a b2_enqueue batch is open");
+    } else if (b.n_tasks) {
+      rc = enqueue_locked(D, b.tasks, b.n_tasks, nullptr, 0, nullptr,
+                          (b.flags & B2_BATCH_INDEPENDENT) != 0);
+    }
+    if (rc == B2_OK) {
+      D->ticket_slot[ti] = (int8_t)D->task_slot;
+      D->ticket_ntasks[ti] = b.n_tasks;
+      {
+        std::lock_guard<std::mutex> ql(D->qmu);
+        D->ticket_phase[ti] = kPhaseTabled;
+        for (auto &c : sub.cancels) tombstone_locked(D, D->task_slot, b.n_tasks, c.first, c.second, false);
+      }
+    } else {
+      submit_fail(D, t, rc);
+      D->ticket_cv.notify_all();
+      return;
+    }
+  }
+  // 3. operand bytes into pinned ingress memory (copy pool; no lock held)
+  rc = run_copy_jobs(D, b.jobs, b.n_jobs);
+  // 4. upload, worker, downloads, ticket
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    cudaSetDevice(D->dev);
+    auto cu = [&](cudaError_t e, const char *what) {
+      if (e != cudaSuccess && rc == B2_OK)
+        rc = fail(B2_E_CUDA, "%s -> %s (b2_submit)", what, cudaGetErrorString(e));
+    };
+    if (rc == B2_OK && b.in_bytes) {
+      if (b.in_off + b.in_bytes > D->h_in_bytes || b.in_off + b.in_bytes > D->arena_bytes[0])
+        rc = fail(B2_E_ARG, "b2_submit: ingress range [%llu, +%llu) out of bounds",
+                  (unsigned long long)b.in_off, (unsigned long long)b.in_bytes);
+      else {
+        cu(cudaMemcpyAsync(D->arena[0] + b.in_off, D->h_in + b.in_off, b.in_bytes,
+                           cudaMemcpyHostToDevice, D->stream), "cudaMemcpyAsync(H2D)");
+        D->stats.bytes_h2d += b.in_bytes;
+      }
+    }
+    if (rc == B2_OK) rc = launch_locked(D, b.n_tasks ? b.status_host_off : UINT64_MAX, t);
+    if (rc == B2_OK && b.out_bytes) {
+      if (b.out_host_off + b.out_bytes > D->h_out_bytes || b.out_dev_off + b.out_bytes > D->arena_bytes[0])
+        rc = fail(B2_E_ARG, "b2_submit: egress range out of bounds");
+      else {
+        rc = egress_after_compute(D);
+        if (rc == B2_OK) {
+          cu(cudaMemcpyAsync(D->h_out + b.out_host_off, D->arena[0] + b.out_dev_off, b.out_bytes,
+                             cudaMemcpyDeviceToHost, D->egress), "cudaMemcpyAsync(D2H)");
+          D->egress_dirty = true;
+          D->stats.bytes_d2h += b.out_bytes;
+        }
+      }
+    }
+    if (rc == B2_OK) rc = record_ticket_event(D, t);
+    if (rc != B2_OK) submit_fail(D, t, rc);
+  }
+  D->ticket_cv.notify_all();
+}
+
+static void submit_loop(Device *D) {
+  for (;;) {
+    Submission sub;
+    {
+      std::unique_lock<std::mutex> lk(D->qmu);
+      D->qcv.wait(lk, [&] { return D->q_stop || !D->queue.empty(); });
+      if (D->queue.empty()) return;   // q_stop and nothing left
+      sub = std::move(D->queue.front());
+      D->queue.pop_front();
+      D->q_busy = true;
+      D->q_current = &sub;
+    }
+    submit_one(D, sub);
+    {
+      std::lock_guard<std::mutex> lk(D->qmu);
+      D->q_busy = false;
+      D->q_current = nullptr;
+    }
+    D->qidle.notify_all();
+  }
+}
+
+int b2_submit(int dev, b2_batch *batch) {
+  if (!batch) return fail(B2_E_ARG, "batch is NULL");
+  if (batch->n_tasks && !batch->tasks) return fail(B2_E_ARG, "batch->tasks is NULL");
+  if (batch->n_jobs && !batch->jobs) return fail(B2_E_ARG, "batch->jobs is NULL");
+  Device *D = get(dev);
+  if (!D) return fail(B2_E_ARG, "device ordinal %d out of range", dev);
+  Submission sub;
+  {
+    std::lock_guard<std::mutex> lk(D->mu);
+    if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev);
+    if (batch->n_tasks > D->qcap)
+      return fail(B2_E_NOMEM, "batch of %u electrons exceeds queue capacity %u", batch->n_tasks, D->qcap);
+    if (D->pend_tasks != 0) return fail(B2_E_STATE, "b2_submit while a b2_enqueue batch is open");
+    sub.ticket = alloc_ticket(D, kPhaseQueued);
+    D->ticket_ntasks[sub.ticket % kTickets] = batch->n_tasks;
+  }
+  batch->ticket = sub.ticket;
+  sub.b = *batch;
+  {
+    std::lock_guard<std::mutex> lk(D->qmu);
+    D->queue.push_back(std::move(sub));
+  }
+  D->qcv.notify_one();
+  return B2_OK;
+}
+
+int b2_cancel(int dev, uint64_t ticket, uint32_t first, uint32_t count) {
+  DEV_OR_FAIL(D, dev);
+  if (ticket == 0 || ticket >= D->next_ticket)
+    return fail(B2_E_ARG, "unknown ticket %llu", (unsigned long long)ticket);
+  if (D->next_ticket - ticket >= (uint64_t)kTickets || count == 0) return B2_OK;   // long done
+  const int i = (int)(ticket % kTickets);
+  std::lock_guard<std::mutex> ql(D->qmu);
+  switch (D->ticket_phase[i]) {
+    case kPhaseQueued:
+      for (auto &sub : D->queue)
+        if (sub.ticket == ticket) {
+          sub.cancels.emplace_back(first, count);
+          return B2_OK;
+        }
+      // taken by the submission thread but not tabled yet: it applies the list when it tables
+      // the batch (under qmu, which we hold)
+      if (D->q_current && D->q_current->ticket == ticket) D->q_current->cancels.emplace_back(first, count);
+      return B2_OK;
+    case kPhaseTabled:
+      return tombstone_locked(D, D->ticket_slot[i], D->ticket_ntasks[i], first, count, false);
+    case kPhaseLaunched:
+      return tombstone_locked(D, D->ticket_slot[i], D->ticket_ntasks[i], first, count, true);
+    default:
+      return B2_OK;
+  }
 }
 
 // ------------------------------------------------------------ peer routing --
@@ -914,7 +1313,7 @@ int b2_ipc_open(int dev, const void *handle64, uint64_t peer_arena_bytes, uint32
 
 int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_off,
                  uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (dst_arena_id >= (uint32_t)D->n_arenas) return fail(B2_E_ARG, "unknown arena id %u", dst_arena_id);
   if (src_off + bytes > D->arena_bytes[0] || dst_off + bytes > D->arena_bytes[dst_arena_id])
     return fail(B2_E_ARG, "peer_copy: range outside arena");
@@ -926,7 +1325,7 @@ int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_
 
 int b2_peer_pack(int dev, uint32_t dst_arena_id, const b2_span *spans, uint32_t n) {
   Range r_("b2_peer_pack");
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   return move_spans_locked(D, spans, n, 0, dst_arena_id);
 }
 
@@ -941,7 +1340,7 @@ int b2_event_create(int dev, uint32_t *event_id) {
 }
 
 int b2_event_record(int dev, uint32_t event_id) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (event_id >= D->n_user_ev) return fail(B2_E_ARG, "unknown event %u", event_id);
   CU(cudaEventRecord(D->user_ev[event_id], D->stream));
   return B2_OK;
@@ -963,7 +1362,7 @@ int b2_event_elapsed_ms(int dev, uint32_t start_id, uint32_t stop_id, float *ms)
 }
 
 int b2_flush_l2(int dev, uint64_t scratch_off, uint64_t bytes) {
-  DEV_OR_FAIL(D, dev);
+  DEV_ORDERED(D, dev);
   if (scratch_off + bytes > D->arena_bytes[0]) return fail(B2_E_ARG, "flush range outside arena");
   static int v = 0;
   CU(cudaMemsetAsync(D->arena[0] + scratch_off, (++v) & 0xff, bytes, D->stream));

@@ -254,6 +254,10 @@ def encode(fn: Callable, args, kwargs) -> EncodedTask:
             raws = tuple(o[0] for o in ops)
             nrows, shape = len(ops), ops[0][1]
         row_bytes = int(np.prod(shape, dtype=np.int64)) * 4
+        if row_bytes == 4 and nrows > 8:
+            # np.sum(np.stack(xs), axis=0) over [K, 1] reduces a contiguous axis: numpy adds
+            # pairwise there, the device adds in row order — the low bits can differ
+            raise NotDeviceEligible("stack_sum rows of a single element reduce pairwise on the host")
         return EncodedTask(spec, raws, (0, 0), row_bytes // 4, nrows, row_bytes,
                            ("array", np.float32, tuple(shape), "C"))
     if k in _INT2 or k in _INT1:

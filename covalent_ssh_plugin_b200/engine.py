@@ -36,12 +36,24 @@ import numpy as np
 from . import _b2lib as L
 from .electrons import DeviceElectron, DeviceRef, EncodedTask, decode, registry_size, registry_snapshot
 
+try:
+    from . import _b2host          # compiled staging helper (hostext/b2host.c)
+except ImportError as _err:        # never a silent fallback: the hot path needs it
+    raise ImportError(
+        "covalent_ssh_plugin_b200._b2host is not built: run `python -m covalent_ssh_plugin_b200.build` "
+        f"({_err})") from _err
+
 _TASK = struct.Struct("<IIQQQQIIIIQ")
 assert _TASK.size == 64
 
 ALIGN = 256                      # payload alignment inside a segment
 SPLIT_BYTES = 1 << 20            # large elementwise electrons are sliced into tasks of this size
 _ELEMENTWISE = (L.K_COPY, L.K_SCALE_ADD, L.K_ADD, L.K_MUL, L.K_AXPY)
+_FAST1 = (L.K_COPY, L.K_SCALE_ADD, L.K_SUM)        # kinds the C stager takes in one call
+_FAST2 = (L.K_ADD, L.K_MUL, L.K_AXPY)
+_FASTI = (L.K_IADD, L.K_IMUL)
+IDX_BITS = _b2host.IDX_BITS
+IDX_MASK = (1 << IDX_BITS) - 1
 MiB = 1 << 20
 
 DEFAULTS = {
@@ -53,11 +65,11 @@ DEFAULTS = {
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
     "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
     "gc_tune": os.environ.get("B2_GC_TUNE", "1") != "0",
-    # operands of at least this many bytes are copied into pinned memory by a small
-    # thread pool (numpy releases the GIL while copying): one host thread moves
-    # ~9-11 GB/s, 8-16 threads 25-40 GB/s (tools/staging_probe.py on the B200 host)
-    "parallel_stage_bytes": int(os.environ.get("B2_PARALLEL_STAGE_BYTES", 512 * 1024)),
-    "stage_threads": int(os.environ.get("B2_STAGE_THREADS", 8)),
+    # general path only: operands of at least this many bytes become copy jobs for the
+    # library's copy threads (one host thread moves ~9-11 GB/s, 8-16 threads 25-40 GB/s,
+    # tools/staging_probe.py on the B200 host); smaller ones are copied on the spot.  The
+    # fast path (stage_fast) always queues jobs.  Thread count: B2_STAGE_THREADS (library).
+    "parallel_stage_bytes": int(os.environ.get("B2_PARALLEL_STAGE_BYTES", 64 * 1024)),
 }
 
 _gc_tuned = False
@@ -96,22 +108,25 @@ def _round_up(n: int, a: int = ALIGN) -> int:
 
 class Batch:
     """Electrons staged together: one ingress segment, one egress segment, one
-    launch, one future."""
+    b2_submit (copies, H2D, worker launch, D2H), one completion ticket."""
 
-    __slots__ = ("engine", "seg", "oseg", "n", "in_used", "out_used", "table", "future", "loop",
+    __slots__ = ("engine", "seg", "oseg", "n", "n_jobs", "in_used", "out_used", "table", "table_mem", "loop",
                  "ticket", "unread", "done", "flushed", "error", "lease", "zero_copy", "out_freed",
-                 "pending", "ship_wanted")
+                 "waiters", "keep", "all_ok", "f32", "in_base", "out_base", "future")
 
     def __init__(self, engine: "DeviceEngine", seg: int, oseg: int, loop):
         self.engine = engine
         self.seg = seg
         self.oseg = oseg
-        self.n = 0
+        self.n = 0                  # task records (while the batch is open the stager holds the truth)
+        self.n_jobs = 0
         self.in_used = 0
         self.out_used = 0
         self.table = engine._tables[seg]
+        self.table_mem = engine._table_mem[seg]
+        self.in_base = seg * engine.seg_bytes
+        self.out_base = oseg * engine.seg_bytes
         self.loop = loop
-        self.future = loop.create_future() if loop is not None else None
         self.ticket = 0
         self.unread = 0
         self.done = False
@@ -120,14 +135,17 @@ class Batch:
         self.lease = None           # ctypes view of the egress segment that result arrays alias
         self.zero_copy = False
         self.out_freed = False
-        self.pending = 0            # operand copies still running in the staging threads
-        self.ship_wanted = False    # flush was requested while copies were pending
+        self.waiters: list = []     # one future per electron awaiting this batch
+        self.keep: list = []        # operand objects the queued copy jobs still read from
+        self.all_ok = False         # every status word of the batch is B2_TS_OK (set on completion)
+        self.f32 = None             # float32 view of the egress segment (zero-copy results are slices of it)
+        self.future = None          # legacy: completed together with the waiters (tests await it)
 
 
 class Staged:
     """Handle of one staged electron (what the executor keeps between steps)."""
 
-    __slots__ = ("batch", "index", "out_off", "out_bytes", "meta", "spec", "parts")
+    __slots__ = ("batch", "index", "out_off", "out_bytes", "meta", "spec", "parts", "cancelled")
 
     def __init__(self, batch: Batch, index: int, out_off: int, out_bytes: int, meta: tuple,
                  spec: DeviceElectron):
@@ -138,6 +156,7 @@ class Staged:
         self.out_bytes = out_bytes
         self.meta = meta
         self.spec = spec
+        self.cancelled = False
 
 
 class Heap:
@@ -228,8 +247,6 @@ class DeviceEngine:
         self.queue_cap = int(c["queue_cap"])
         self.zero_copy = bool(c["zero_copy"])
         self.parallel_stage_bytes = int(c["parallel_stage_bytes"])
-        self._stage_threads = max(1, int(c["stage_threads"]))
-        self._stage_pool = None
         if self.max_batch > self.queue_cap:
             self.max_batch = self.queue_cap
         staging = int(c["staging_bytes"])
@@ -253,7 +270,18 @@ class DeviceEngine:
         L.call("b2_get_info", ordinal, C.byref(self.info))
         self._h_in, _ = self._host_view(0, self.staging_in)
         self._h_out, self._h_out_addr = self._host_view(1, self.staging_out)
-        self._tables = [bytearray(64 * self.max_batch) for _ in range(self.n_segments)]
+        self._h_out_f32 = self._h_out[:self.staging_out & ~3].view(np.float32)
+        # per ingress segment: the batch's task table, copy-job list and b2_batch descriptor.
+        # They belong to the batch that owns the segment and must stay valid until its ticket
+        # completes — which is exactly when the segment returns to the pool.
+        self._tables = [np.zeros(self.max_batch, dtype=L.TASK_DTYPE) for _ in range(self.n_segments)]
+        self._table_mem = [memoryview(t).cast("B") for t in self._tables]
+        self._tables_addr = [t.ctypes.data for t in self._tables]
+        self._cap_jobs = 2 * self.max_batch + 64
+        self._jobs = [np.zeros(self._cap_jobs, dtype=L.JOB_DTYPE) for _ in range(self.n_segments)]
+        self._jobs_addr = [j.ctypes.data for j in self._jobs]
+        self._descs = [L.Batch() for _ in range(self.n_segments)]
+        self._stager = _b2host.Stager(np.ndarray)
         self._free_segments = list(range(self.n_segments - 1, -1, -1))
         self._free_out = list(range(self.n_out_segments - 1, -1, -1))
         self._seg_lock = threading.Lock()          # lease finalizers may run on any thread
@@ -317,19 +345,16 @@ class DeviceEngine:
         raise MemoryError("no free staging segment (results of earlier electrons still hold all of them)")
 
     def _copy_into_pinned(self, jobs) -> None:
-        big = [j for j in jobs if j[1].size >= self.parallel_stage_bytes]
-        if len(big) > 1:
-            if self._stage_pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-
-                self._stage_pool = ThreadPoolExecutor(self._stage_threads, thread_name_prefix="b2-stage")
-            small = [j for j in jobs if j[1].size < self.parallel_stage_bytes]
-            futs = [self._stage_pool.submit(self._run_copies, [j]) for j in big]
-            self._run_copies(small)
-            for f in futs:
-                f.result()
-        else:
-            self._run_copies(jobs)
+        """(ingress offset, flat uint8 array) pairs -> pinned ingress memory, on the library's
+        copy threads (b2_stage_copy; synchronous)."""
+        jobs = [j for j in jobs if j[1].size]
+        if not jobs:
+            return
+        tab = np.zeros(len(jobs), dtype=L.JOB_DTYPE)
+        tab["src"] = [j[1].ctypes.data for j in jobs]
+        tab["dst_off"] = [j[0] for j in jobs]
+        tab["bytes"] = [j[1].size for j in jobs]
+        L.call("b2_stage_copy", self.ordinal, tab.ctypes.data, len(jobs))
 
     def put_many(self, arrays) -> List["DeviceArray"]:
         """Host ndarrays -> heap slots: per staging segment one H2D + one unpack launch."""
@@ -427,7 +452,7 @@ class DeviceEngine:
             finally:
                 with self._seg_lock:
                     self._free_out.append(oseg)
-                self._wake_one()
+                self._wake_waiters()
         return results
 
     def peer_arena_id(self, other_ordinal: int) -> int:
@@ -508,68 +533,20 @@ class DeviceEngine:
         return s
 
     # --------------------------------------------------------------- staging --
+    def _need_in(self, enc: EncodedTask) -> int:
+        """Ingress bytes ``_append`` will consume for this electron (the one formula
+        ``fits``, ``stage`` and ``_append`` share)."""
+        if enc.nrows and enc.spec.kind == L.K_STACK_SUM:
+            return _round_up(_round_up(enc.count * 4, 16) * enc.nrows)     # rows at a 16 B aligned stride
+        need = 0
+        for p in enc.payloads:
+            if type(p) is not DeviceRef:
+                need += _round_up(p.size)
+        return need
+
     def fits(self, enc: EncodedTask) -> bool:
-        need_in = 0
-        for p in enc.payloads:
-            if type(p) is not DeviceRef:
-                need_in += _round_up(p.size)
-        return need_in <= self.seg_bytes and _round_up(max(enc.out_bytes, 16)) <= self.out_data_bytes
-
-    async def stage(self, enc: EncodedTask) -> Staged:
-        """Copy one electron's operands into pinned ingress memory and append
-        its task record to the open batch (ssh.py:147-150 + ssh.py:360-361)."""
-        need_in = 0
-        for p in enc.payloads:
-            if type(p) is not DeviceRef:
-                need_in += _round_up(p.size)
-        need_out = _round_up(max(enc.out_bytes, 16))
-        if need_in > self.seg_bytes or need_out > self.out_data_bytes:
-            raise ValueError("electron payload larger than one staging segment")
-        loop = asyncio.get_running_loop()
-        while True:
-            b = self._open
-            if b is not None and (b.n >= self.max_batch or b.in_used + need_in > self.seg_bytes
-                                  or b.out_used + need_out > self.out_data_bytes or b.loop is not loop):
-                self.flush()
-                b = None
-            if b is None:
-                pair = self._take_segments()
-                if pair is None:
-                    self._reap()
-                    pair = self._take_segments()
-                if pair is None:
-                    fut = loop.create_future()
-                    self._segment_waiters.append((loop, fut))
-                    await fut
-                    continue
-                b = Batch(self, pair[0], pair[1], loop)
-                self._open = b
-                loop.call_soon(self._idle_flush, b)
-            break
-        if need_in < self.parallel_stage_bytes:
-            return self._append(b, enc, None)
-        # Large operands: reserve the space and write the task record now, let the
-        # staging threads do the copies, and hold the batch back until they are done.
-        jobs: list = []
-        staged = self._append(b, enc, jobs)
-        if jobs:
-            if self._stage_pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-
-                self._stage_pool = ThreadPoolExecutor(self._stage_threads, thread_name_prefix="b2-stage")
-            b.pending += 1
-            try:
-                await loop.run_in_executor(self._stage_pool, self._run_copies, jobs)
-            finally:
-                b.pending -= 1
-                if b.pending == 0 and b.ship_wanted:
-                    self._ship(b)
-        return staged
-
-    def _run_copies(self, jobs) -> None:
-        h_in = self._h_in
-        for off, p in jobs:
-            h_in[off:off + p.size] = p
+        return (self._need_in(enc) <= self.seg_bytes
+                and _round_up(max(enc.out_bytes, 16)) <= self.out_data_bytes)
 
     def _take_segments(self):
         with self._seg_lock:
@@ -577,23 +554,128 @@ class DeviceEngine:
                 return self._free_segments.pop(), self._free_out.pop()
         return None
 
-    def _append(self, b: Batch, enc: EncodedTask, jobs) -> Staged:
+    def _open_batch(self, loop) -> Optional[Batch]:
+        """A fresh open batch bound to ``loop`` (None when no staging segment pair is free)."""
+        pair = self._take_segments()
+        if pair is None:
+            self._reap()
+            pair = self._take_segments()
+            if pair is None:
+                return None
+        b = Batch(self, pair[0], pair[1], loop)
+        self._open = b
+        self._stager.begin(self._jobs_addr[b.seg], self._cap_jobs, self._tables_addr[b.seg], self.max_batch,
+                           b.in_base, self.seg_bytes, self.egress_base + b.out_base, self.out_data_bytes)
+        if loop is not None:
+            loop.call_soon(self._idle_flush, b, -1)
+        return b
+
+    def _pull(self, b: Batch) -> None:
+        """Counters of the open batch: stager -> Batch (before Python-side staging / shipping)."""
+        b.n, b.n_jobs, b.in_used, b.out_used = self._stager.state()
+
+    def stage_fast(self, loop, spec: DeviceElectron, args):
+        """The common case in one C call: a registered one-/two-array or int64 electron whose
+        operands are plain C-contiguous float32 ndarrays (or Python ints).  Writes the task record
+        and the copy job(s) into the open batch and returns ``(batch, packed)`` with
+        ``packed = out_off << IDX_BITS | index``; returns None when the general path
+        (``encode`` + ``stage``) has to look at this call."""
+        kind = spec.kind
+        nargs = len(args)
+        st = self._stager
+        b = self._open
+        if b is None or b.loop is not loop:
+            if b is not None:
+                self.flush()
+            b = self._open_batch(loop)
+            if b is None:
+                return None
+        if spec.fn_id > self._registered:
+            self.sync_registry()
+        for _ in range(2):
+            if kind in _FAST1 and nargs == 1:
+                r = st.stage1(spec.fn_id, kind, args[0])
+            elif kind in _FAST2 and nargs == 2:
+                r = st.stage2(spec.fn_id, args[0], args[1])
+            elif kind in _FASTI and nargs == 2:
+                r = st.stage_int(spec.fn_id, args[0], args[1])
+            elif kind == L.K_ISCALE_ADD and nargs == 1:
+                r = st.stage_int(spec.fn_id, args[0], 0)
+            else:
+                return None
+            if r >= 0:
+                b.keep.append(args)
+                b.unread += 1
+                return b, r
+            if r != _b2host.FULL:
+                return None
+            self.flush()                       # the open batch is full: ship it, retry in a new one
+            b = self._open_batch(loop)
+            if b is None:
+                return None
+        return None
+
+    def waiter(self, b: Batch, loop):
+        """A future of ``loop`` that completes when batch ``b`` has (one per electron: cancelling
+        one ``run()`` must never cancel its batch-mates)."""
+        fut = loop.create_future()
+        b.waiters.append(fut)
+        return fut
+
+    async def stage(self, enc: EncodedTask) -> Staged:
+        """General path: copy (or queue the copy of) one electron's operands into pinned
+        ingress memory and append its task record to the open batch (ssh.py:147-150 +
+        ssh.py:360-361).  Waits for a staging segment pair when none is free."""
+        need_in = self._need_in(enc)
+        need_out = _round_up(max(enc.out_bytes, 16))
+        if need_in > self.seg_bytes or need_out > self.out_data_bytes:
+            raise ValueError("electron payload larger than one staging segment")
+        loop = asyncio.get_running_loop()
+        while True:
+            b = self._open
+            if b is not None:
+                self._pull(b)
+                if (b.n >= self.max_batch or b.in_used + need_in > self.seg_bytes
+                        or b.out_used + need_out > self.out_data_bytes or b.loop is not loop
+                        or b.n_jobs + len(enc.payloads) > self._cap_jobs):
+                    self.flush()
+                    b = None
+            if b is None:
+                b = self._open_batch(loop)
+                if b is None:
+                    fut = loop.create_future()
+                    self._segment_waiters.append((loop, fut))
+                    await fut
+                    continue
+            break
+        return self._append(b, enc)
+
+    def _copy_in(self, b: Batch, off: int, p: np.ndarray) -> None:
+        """One operand into pinned ingress memory at ``off``: small ones right here, large ones
+        as a copy job for the library's copy threads (they run when the batch ships)."""
+        if p.size < self.parallel_stage_bytes:
+            self._h_in[off:off + p.size] = p
+        else:
+            if self._stager.add_job(p.ctypes.data, off, p.size) < 0:
+                self._h_in[off:off + p.size] = p
+            else:
+                b.keep.append(p)
+
+    def _append(self, b: Batch, enc: EncodedTask) -> Staged:
         """Reserve staging space, copy (or queue the copy of) the operands, write the
-        task record.  ``jobs`` collects (offset, payload) pairs instead of copying."""
+        task record(s).  ``b`` is the open batch; its counters live in the stager."""
         spec = enc.spec
         if spec.fn_id > self._registered:
             self.sync_registry()
-        seg_base = b.seg * self.seg_bytes
+        self._pull(b)
+        seg_base = b.in_base
         h_in = self._h_in
         flags = 0
         payloads = enc.payloads
         if len(payloads) == 1 and not enc.nrows and type(payloads[0]) is not DeviceRef:
             p = payloads[0]                               # the common case, kept short
             a0 = seg_base + b.in_used
-            if jobs is None:
-                h_in[a0:a0 + p.size] = p
-            else:
-                jobs.append((a0, p))
+            self._copy_in(b, a0, p)
             b.in_used += _round_up(p.size)
             a1 = 0
         elif not payloads:
@@ -607,13 +689,13 @@ class DeviceEngine:
             if len(payloads) == 1:
                 rows = payloads[0].reshape(enc.nrows, row_bytes)
                 if stride == row_bytes:
-                    h_in[a0:a0 + rows.size] = payloads[0]
+                    self._copy_in(b, a0, payloads[0])
                 else:
                     for r in range(enc.nrows):
                         h_in[a0 + r * stride:a0 + r * stride + row_bytes] = rows[r]
             else:
                 for r, p in enumerate(payloads):
-                    h_in[a0 + r * stride:a0 + r * stride + p.size] = p
+                    self._copy_in(b, a0 + r * stride, p)
             b.in_used += _round_up(stride * enc.nrows)
         else:
             offs = []
@@ -624,18 +706,17 @@ class DeviceEngine:
                         flags |= self.peer_arena_id(p.ordinal) << (L.F_ARENA0_SHIFT, L.F_ARENA1_SHIFT)[i]
                     continue
                 o = seg_base + b.in_used
-                if jobs is None:
-                    h_in[o:o + p.size] = p
-                else:
-                    jobs.append((o, p))
+                self._copy_in(b, o, p)
                 offs.append(o)
                 b.in_used += _round_up(p.size)
             a0, a1 = offs[0], (offs[1] if len(offs) > 1 else 0)
+        assert b.in_used <= self.seg_bytes, "staging budget and staging layout disagree"
         out_off = b.out_used                                 # inside the egress segment
         b.out_used = out_off + _round_up(max(enc.out_bytes, 16))
         idx = b.n
-        out_dev = self.egress_base + b.oseg * self.seg_bytes + out_off
+        out_dev = self.egress_base + b.out_base + out_off
         parts = 1
+        mem = b.table_mem
         if enc.out_bytes >= 2 * SPLIT_BYTES and spec.kind in _ELEMENTWISE and not (flags & L.F_IMM0):
             # One electron = one CTA on the device.  A batch of a few very large electrons would
             # leave most of the 592 resident CTAs idle, so a large elementwise electron goes out
@@ -653,60 +734,72 @@ class DeviceEngine:
                 while done < total:
                     n_el = min(per, total - done)
                     o = done * esz
-                    _TASK.pack_into(b.table, (idx + k) * 64, spec.fn_id, flags, a0 + o,
+                    _TASK.pack_into(mem, (idx + k) * 64, spec.fn_id, flags, a0 + o,
                                     (a1 + o) if two else a1, out_dev + o, n_el, 0, 0, 0, 0, 0)
                     done += n_el
                     k += 1
                 parts = k
         if parts <= 1:
             parts = 1
-            _TASK.pack_into(b.table, idx * 64, spec.fn_id, flags, a0, a1, out_dev, enc.count, enc.nrows,
+            _TASK.pack_into(mem, idx * 64, spec.fn_id, flags, a0, a1, out_dev, enc.count, enc.nrows,
                             0, 0, 0, 0)
         b.n = idx + parts
         b.unread += 1
+        _, n_jobs, _, _ = self._stager.state()                # add_job may have advanced it
+        self._stager.set_state(b.n, n_jobs, b.in_used, b.out_used)
         st = Staged(b, idx, out_off, enc.out_bytes, enc.result_meta, spec)
         st.parts = parts
         return st
 
-    def _idle_flush(self, b: Batch) -> None:
-        if self._open is b and not b.flushed:
-            self.flush()
+    def _idle_flush(self, b: Batch, seen: int) -> None:
+        """Ships the open batch once a whole event-loop iteration has passed without it
+        growing.  (Shipping on the first idle callback after opening cut batches short
+        whenever the electrons that were about to join were still queued behind it — e.g.
+        stagers woken by a segment release, whose wake-ups are scheduled after this callback.)"""
+        if self._open is not b or b.flushed:
+            return
+        n = self._stager.state()[0]
+        if n != seen:
+            b.loop.call_soon(self._idle_flush, b, n)
+            return
+        self.flush()
 
     def flush(self) -> Optional[Batch]:
-        """Ship the open batch: H2D, worker launch, D2H, completion ticket."""
+        """Ship the open batch: one b2_submit (copies, H2D, worker launch, D2H, ticket)."""
         b = self._open
         if b is None:
             return None
         self._open = None
+        self._pull(b)
+        self._stager.end()
         if b.n == 0:
             self._release_in(b.seg)
             self._release_out(b)
             return None
-        if b.pending:                  # staging threads are still filling this batch
-            b.ship_wanted = True
-            return b
         return self._ship(b)
 
     def _ship(self, b: Batch) -> Batch:
         b.flushed = True
-        b.ship_wanted = False
-        dev = self.ordinal
-        in_base = b.seg * self.seg_bytes
-        out_base = b.oseg * self.seg_bytes
-        status_off = out_base + self.out_data_bytes
+        status_off = b.out_base + self.out_data_bytes
         # results alias pinned memory only while the egress pool is comfortable
         with self._seg_lock:
             b.zero_copy = self.zero_copy and len(self._free_out) * 4 >= self.n_out_segments
+        d = self._descs[b.seg]
+        d.jobs = self._jobs_addr[b.seg]
+        d.tasks = self._tables_addr[b.seg]
+        d.n_jobs = b.n_jobs
+        d.n_tasks = b.n
+        d.flags = L.BATCH_INDEPENDENT              # run() electrons carry no dependency edges
+        d.in_off = b.in_base
+        d.in_bytes = b.in_used
+        d.status_host_off = status_off
+        d.out_dev_off = self.egress_base + b.out_base
+        d.out_host_off = b.out_base
+        d.out_bytes = b.out_used
+        d.ticket = 0
         try:
-            if b.in_used:
-                L.call("b2_h2d", dev, in_base, in_base, b.in_used)
-            tab = (C.c_char * (64 * b.n)).from_buffer(b.table)
-            L.call("b2_enqueue", dev, C.addressof(tab), b.n, None, 0, None)
-            t = C.c_uint64()
-            L.call("b2_launch", dev, status_off, C.byref(t))
-            L.call("b2_d2h", dev, self.egress_base + out_base, out_base, b.out_used)
-            L.call("b2_mark", dev, C.byref(t))
-            b.ticket = t.value
+            L.call("b2_submit", self.ordinal, C.byref(d))
+            b.ticket = d.ticket
         except BaseException as err:  # surface on the awaiting coroutines
             b.error = err
             self._complete(b)
@@ -717,7 +810,6 @@ class DeviceEngine:
         self.counters["bytes_out"] += b.out_used
         self._inflight.append(b)
         self._waitq.put(b)
-        self._reap()
         return b
 
     # ------------------------------------------------------------ completion --
@@ -747,31 +839,72 @@ class DeviceEngine:
                 b.error = err
             try:
                 b.loop.call_soon_threadsafe(self._complete, b)
-            except RuntimeError:      # loop already closed
+            except (RuntimeError, AttributeError):      # loop already closed / no loop
                 self._complete(b)
 
     def _complete(self, b: Batch) -> None:
         if b.done:
             return
         b.done = True
+        b.keep = []                   # the copy jobs have run: operands may go
         self._release_in(b.seg)       # the copies out of pinned ingress have finished
+        if b.error is None:
+            words = self._h_out[b.out_base + self.out_data_bytes:
+                                b.out_base + self.out_data_bytes + 4 * b.n].view(np.uint32)
+            b.all_ok = bool((words == L.TS_OK).all())
         if b.error is not None or b.unread == 0:
             self._release_out(b)
-        fut = b.future
-        if fut is not None and not fut.done():
-            if b.error is not None:
-                fut.set_exception(b.error)
-            else:
-                fut.set_result(b)
+        waiters, b.waiters = b.waiters, []
+        for fut in waiters:
+            if not fut.done():
+                fut.set_result(None)
 
     def status_of(self, s: Staged) -> int:
         b = s.batch
-        off = b.oseg * self.seg_bytes + self.out_data_bytes + 4 * s.index
+        if b.all_ok:
+            return L.TS_OK
+        off = b.out_base + self.out_data_bytes + 4 * s.index
         if s.parts == 1:
             return int(self._h_out[off:off + 4].view(np.uint32)[0])
         words = self._h_out[off:off + 4 * s.parts].view(np.uint32)
         bad = words[words != L.TS_OK]
         return int(bad[0]) if len(bad) else L.TS_OK
+
+    def status_at(self, b: Batch, index: int) -> int:
+        off = b.out_base + self.out_data_bytes + 4 * index
+        return int(self._h_out[off:off + 4].view(np.uint32)[0])
+
+    def _lease_of(self, b: Batch):
+        lease = b.lease
+        if lease is None:
+            lease = (C.c_uint8 * self.out_data_bytes).from_address(self._h_out_addr + b.out_base)
+            fin = weakref.finalize(lease, self._lease_dropped, b.oseg)
+            fin.atexit = False
+            b.lease = lease
+            b.f32 = np.frombuffer(lease, dtype=np.float32)
+            with self._seg_lock:
+                self._leases_out += 1
+            self.counters["zero_copy_batches"] += 1
+        return lease
+
+    def array_result(self, b: Batch, out_off: int, count: int) -> np.ndarray:
+        """1-D float32 result of ``count`` elements at ``out_off`` of the batch's egress segment:
+        a zero-copy slice of pinned memory when the pool has room, else a copy."""
+        o4 = out_off >> 2
+        if b.zero_copy and count:
+            if b.lease is None:
+                self._lease_of(b)
+            return b.f32[o4:o4 + count]
+        base4 = b.out_base >> 2
+        return self._h_out_f32[base4 + o4:base4 + o4 + count].copy()
+
+    def int_result(self, b: Batch, out_off: int) -> int:
+        o = b.out_base + out_off
+        return int(self._h_out[o:o + 8].view(np.int64)[0])
+
+    def f32_result(self, b: Batch, out_off: int):
+        o = b.out_base + out_off
+        return np.float32(self._h_out[o:o + 4].view(np.float32)[0])
 
     def result_of(self, s: Staged) -> Any:
         """Materialise one result (ssh.py:451-456).  Array results alias the
@@ -779,35 +912,38 @@ class DeviceEngine:
         faults); the segment returns to the pool when the last such array dies.
         Otherwise they are copied out."""
         b = s.batch
-        base = b.oseg * self.seg_bytes
         meta = s.meta
         if b.zero_copy and meta[0] == "array" and s.out_bytes:
-            lease = b.lease
-            if lease is None:
-                lease = (C.c_uint8 * self.out_data_bytes).from_address(self._h_out_addr + base)
-                fin = weakref.finalize(lease, self._lease_dropped, b.oseg)
-                fin.atexit = False
-                b.lease = lease
-                with self._seg_lock:
-                    self._leases_out += 1
-                self.counters["zero_copy_batches"] += 1
-            arr = np.frombuffer(lease, dtype=meta[1], count=s.out_bytes // 4, offset=s.out_off)
+            arr = self.array_result(b, s.out_off, s.out_bytes // 4)
             return arr.reshape(meta[2], order=meta[3])
-        off = base + s.out_off
+        off = b.out_base + s.out_off
         return decode(meta, self._h_out[off:off + max(s.out_bytes, 16)])
 
     def release(self, s: Staged) -> None:
         """The caller is done with this electron's staging (ssh.py:284-315)."""
-        b = s.batch
+        self.release_one(s.batch)
+
+    def release_one(self, b: Batch) -> None:
         b.unread -= 1
         if b.unread == 0 and b.done:
             self._release_out(b)
+
+    def cancel_slots(self, b: Batch, index: int, parts: int = 1) -> None:
+        """Tombstone task records [index, index+parts) of batch ``b`` (the
+        reference cannot cancel, ssh.py:460-464): directly in the table while the batch is
+        still open, through ``b2_cancel`` once it has been submitted."""
+        if b.done:
+            return
+        if not b.flushed:
+            b.table["flags"][index:index + parts] |= L.F_CANCELLED
+        else:
+            L.call("b2_cancel", self.ordinal, b.ticket, index, parts)
 
     # -------------------------------------------------------- segment pools ---
     def _release_in(self, seg: int) -> None:
         with self._seg_lock:
             self._free_segments.append(seg)
-        self._wake_one()
+        self._wake_waiters()
 
     def _release_out(self, b: Batch) -> None:
         """Egress segment back to the pool — unless result arrays alias it, in
@@ -816,11 +952,12 @@ class DeviceEngine:
             return
         b.out_freed = True
         if b.lease is not None:
-            b.lease = None            # drop the batch's own reference; arrays keep theirs
+            b.lease = None            # drop the batch's own references; arrays keep theirs
+            b.f32 = None
             return
         with self._seg_lock:
             self._free_out.append(b.oseg)
-        self._wake_one()
+        self._wake_waiters()
 
     def _lease_dropped(self, oseg: int) -> None:
         if self.closed:
@@ -828,9 +965,11 @@ class DeviceEngine:
         with self._seg_lock:
             self._free_out.append(oseg)
             self._leases_out -= 1
-        self._wake_one()
+        self._wake_waiters()
 
-    def _wake_one(self) -> None:
+    def _wake_waiters(self) -> None:
+        """A segment came back: wake EVERY stager parked on the pool.  The first one opens a
+        batch, the others join it — waking one at a time shipped one-electron batches."""
         while self._segment_waiters:
             try:
                 loop, fut = self._segment_waiters.pop(0)
@@ -842,7 +981,6 @@ class DeviceEngine:
                 loop.call_soon_threadsafe(_resolve, fut)
             except RuntimeError:
                 continue
-            return
 
     # ----------------------------------------------------------------- close --
     def close(self) -> None:
@@ -851,8 +989,6 @@ class DeviceEngine:
         self._waitq.put(None)
         if self._waiter is not threading.current_thread():
             self._waiter.join(timeout=10)      # it may be inside b2_wait on an event we are about to destroy
-        if self._stage_pool is not None:
-            self._stage_pool.shutdown(wait=True)
         try:
             L.call("b2_sync", self.ordinal)
         finally:

@@ -36,8 +36,8 @@ from pathlib import Path
 from typing import Any, Callable, Coroutine, Dict, Optional, Tuple, Union
 
 from . import _b2lib, hostpool
-from .electrons import NotDeviceEligible, encode
-from .engine import DeviceEngine, Staged, get_engine
+from .electrons import ATTR as _ELECTRON_ATTR, NotDeviceEligible, encode
+from .engine import IDX_BITS, IDX_MASK, DeviceEngine, Staged, get_engine
 
 try:  # the real Covalent SDK, when installed
     from covalent._shared_files import logger as _cov_logger
@@ -51,6 +51,13 @@ except Exception:  # stand-ins with the same call surface
     from ._covalent_compat import RemoteExecutor, app_log, get_config, log_stack_info
 
     HAVE_COVALENT = False
+
+try:
+    from covalent._shared_files.exceptions import TaskCancelledError
+except Exception:
+    class TaskCancelledError(Exception):
+        """Raised by ``run`` for an electron that ``cancel`` tombstoned (the name Covalent
+        core uses for the same event)."""
 
 EXECUTOR_PLUGIN_NAME = "SSHExecutor"
 
@@ -108,17 +115,22 @@ def resolve_device(hostname: str) -> int:
 # reused for one second so that a 10 000-electron fan-out does not issue 20 000
 # stat calls.  A negative answer is never cached.
 _KEY_TTL = 1.0
-_key_seen: Dict[str, float] = {}
+_key_seen: Dict[tuple, float] = {}       # (path, which check) -> when it last passed
+_key_is_file: Dict[str, float] = {}      # path -> when os.path.isfile last passed (implies exists)
 
 
 def _key_file_present(path: str, check) -> bool:
     now = time.monotonic()
-    if now - _key_seen.get(path, -1e9) < _KEY_TTL:
+    key = (path, check)                  # exists() and isfile() answer different questions
+    if now - _key_seen.get(key, -1e9) < _KEY_TTL:
         return True
     if check(path):
-        _key_seen[path] = now
+        _key_seen[key] = now
+        if check is os.path.isfile:
+            _key_is_file[path] = now
         return True
-    _key_seen.pop(path, None)
+    _key_seen.pop(key, None)
+    _key_is_file.pop(path, None)
     return False
 
 
@@ -159,12 +171,13 @@ class _InFlight:
     """Book-keeping for one electron between the helper calls of ``run``; keyed
     by the same artefact names the reference uses as file names."""
 
-    __slots__ = ("encoded", "staged", "reason", "host_call", "host_result", "rewrap")
+    __slots__ = ("encoded", "staged", "reason", "host_call", "host_result", "rewrap", "live_key")
 
     def __init__(self, encoded=None, reason: str = ""):
         self.encoded = encoded
         self.staged: Optional[Staged] = None
         self.reason = reason
+        self.live_key = None         # (hostname, dispatch_id, node_id) while cancellable
         self.host_call = None        # (fn, args, kwargs, workdir) when the opt-in host pool takes it
         self.host_result = None      # (result, exception) from the host pool
         self.rewrap = None           # Covalent's TransportableObject class, when the call came wrapped in it
@@ -172,6 +185,18 @@ class _InFlight:
 
 # name (any of the five artefact names) -> _InFlight; process-wide like a cache dir
 _inflight: Dict[str, _InFlight] = {}
+
+# (hostname, dispatch_id, node_id) -> (batch, first task index, task records, waiter future) of every
+# electron currently waiting for its batch: what ``cancel`` tombstones.  Module level, like
+# the engines: executor attributes stay plain data.
+_live: Dict[tuple, tuple] = {}
+_CANCELLED = object()                # waiter result that means "tombstoned by cancel()"
+
+_STATUS_TEXT = {_b2lib.TS_OVERFLOW: "integer result does not fit int64",
+                _b2lib.TS_BAD_FN: "no device callback registered for this electron",
+                _b2lib.TS_BAD_ARG: "operand rejected by the device callback",
+                _b2lib.TS_CANCELLED: "cancelled"}
+_ARRAY_KINDS = (_b2lib.K_COPY, _b2lib.K_SCALE_ADD, _b2lib.K_ADD, _b2lib.K_MUL, _b2lib.K_AXPY)
 
 
 class SSHExecutor(RemoteExecutor):
@@ -368,15 +393,25 @@ class SSHExecutor(RemoteExecutor):
         staged = entry.staged
         batch = staged.batch
         if not batch.done:
-            await batch.future
-        elif batch.error is not None:
+            loop = asyncio.get_running_loop()
+            fut = conn.engine.waiter(batch, loop)      # own future: a cancelled run() never cancels batch-mates
+            key = entry.live_key
+            if key is not None:
+                _live[key] = (batch, staged.index, staged.parts, fut)
+            try:
+                if await fut is _CANCELLED:
+                    staged.cancelled = True
+            finally:
+                if key is not None:
+                    _live.pop(key, None)
+        if staged.cancelled:
+            raise TaskCancelledError(f"electron {remote_script_file} was cancelled")
+        if batch.error is not None:
             raise batch.error
         status = conn.engine.status_of(staged)
         if status == _b2lib.TS_OK:
             return _COMPLETED_OK
-        what = {_b2lib.TS_OVERFLOW: "integer result does not fit int64",
-                _b2lib.TS_BAD_FN: "no device callback registered for this electron",
-                _b2lib.TS_BAD_ARG: "operand rejected by the device callback"}.get(status, "device error")
+        what = _STATUS_TEXT.get(status, "device error")
         return CompletedElectron(int(status) or 1, f"{staged.spec.name}: {what} (status {status})")
 
     async def get_status(self, conn: DeviceConnection, remote_result_file: str) -> bool:
@@ -428,13 +463,107 @@ class SSHExecutor(RemoteExecutor):
             conn.engine.release(entry.staged)
             entry.staged = None
 
-    async def cancel(self) -> bool:
-        """Unsupported, as in the reference (ssh.py:460-464)."""
-        raise NotImplementedError("Not implemented as it is unsupported for now")
+    async def cancel(self, task_metadata: Optional[Dict] = None, job_handle: Any = None) -> bool:
+        """Cancel electrons of this executor that are waiting for their batch: the one named by
+        ``task_metadata`` (``dispatch_id``/``node_id``), or all of them when it is None.
+
+        The reference cannot do this (ssh.py:460-464 raises ``NotImplementedError``: a remote
+        interpreter, once spawned, is out of reach).  Here an electron is a task record: it is
+        tombstoned — in the staged table if its batch has not shipped, through ``b2_cancel`` if
+        it is on the device (the worker then skips it and reports ``B2_TS_CANCELLED``; an
+        electron the worker already ran keeps its slot but its result is discarded) — and its
+        ``run()`` raises ``TaskCancelledError``.  Returns True if anything was cancelled."""
+        want = None
+        if task_metadata is not None:
+            want = (task_metadata["dispatch_id"], task_metadata["node_id"])
+        hit = False
+        for key in [k for k in _live if k[0] == self.hostname and (want is None or k[1:] == want)]:
+            entry = _live.pop(key, None)
+            if entry is None:
+                continue
+            batch, index, parts, fut = entry
+            batch.engine.cancel_slots(batch, index, parts)
+            if not fut.done():
+                fut.set_result(_CANCELLED)
+            hit = True
+        return hit
 
     # ------------------------------------------------------------------ run ---
+    def _helpers_untouched(self) -> bool:
+        """True when no helper ``run`` awaits has been monkey-patched or overridden (class or
+        instance): only then may ``run`` take the fused path, which inlines them."""
+        c = type(self)
+        return (c._validate_credentials is _ORIG[0] and c._client_connect is _ORIG[1]
+                and c._write_function_files is _ORIG[2] and c._upload_task is _ORIG[3]
+                and c.submit_task is _ORIG[4] and c._poll_task is _ORIG[5]
+                and c.query_result is _ORIG[6] and c.cleanup is _ORIG[7]
+                and c.get_status is _ORIG[8] and c._attempt_client_connect is _ORIG[9]
+                and _HELPER_NAMES.isdisjoint(self.__dict__))
+
     async def run(self, function: Callable, args: list, kwargs: dict, task_metadata: Dict) -> Coroutine:
-        """Execute one electron and return its result (ssh.py:466-591)."""
+        """Execute one electron and return its result (ssh.py:466-591).
+
+        Two bodies with one behaviour.  The step-by-step body below mirrors the reference's
+        sequence of awaited helpers, so that tests (and subclasses) which patch a helper see
+        exactly the reference's control flow.  When nothing is patched, a registered electron
+        with plain arguments takes the fused body first: the same checks and decisions, inlined
+        — one C call to stage, one suspension until the batch retires — because eight awaited
+        coroutines per electron cost more than the GPU work."""
+        spec = getattr(function, _ELECTRON_ATTR, None)
+        if spec is not None and not kwargs and self.do_cleanup and self._helpers_untouched():
+            # steps 1-2 (ssh.py:493-505): the key file must exist; the "connection" must be open
+            key_file = self.ssh_key_file
+            seen = _key_is_file.get(key_file)
+            if seen is None or time.monotonic() - seen >= _KEY_TTL:
+                await self._validate_credentials()          # raises exactly as the stepwise body would
+            conn = _conn_by_host.get(self.hostname)
+            if conn is not None and not conn.engine.closed:
+                engine = conn.engine
+                loop = asyncio.get_running_loop()
+                got = engine.stage_fast(loop, spec, args)
+                if got is not None:
+                    batch, packed = got
+                    index = packed & IDX_MASK
+                    live_key = (self.hostname, task_metadata["dispatch_id"], task_metadata["node_id"])
+                    outcome = None
+                    if not batch.done:
+                        fut = loop.create_future()
+                        batch.waiters.append(fut)
+                        _live[live_key] = (batch, index, 1, fut)
+                        try:
+                            outcome = await fut
+                        except BaseException:
+                            engine.release_one(batch)
+                            raise
+                        finally:
+                            _live.pop(live_key, None)
+                    if outcome is _CANCELLED:
+                        engine.release_one(batch)
+                        raise TaskCancelledError(f"electron {live_key[1]}_{live_key[2]} was cancelled")
+                    if batch.error is not None:
+                        engine.release_one(batch)
+                        raise batch.error
+                    if not batch.all_ok:
+                        status = engine.status_at(batch, index)
+                        if status != _b2lib.TS_OK:
+                            engine.release_one(batch)
+                            what = _STATUS_TEXT.get(status, "device error")
+                            message = f"{spec.name}: {what} (status {status})"
+                            app_log.warning(message)
+                            return self._on_ssh_fail(function, args, kwargs, message)
+                    kind = spec.kind
+                    if kind in _ARRAY_KINDS:
+                        x = args[0]
+                        result = engine.array_result(batch, packed >> IDX_BITS, x.size)
+                        if x.ndim != 1:
+                            result = result.reshape(x.shape)
+                    elif kind == _b2lib.K_SUM:
+                        result = engine.f32_result(batch, packed >> IDX_BITS)
+                    else:
+                        result = engine.int_result(batch, packed >> IDX_BITS)
+                    engine.release_one(batch)
+                    return result
+
         dispatch_id = task_metadata["dispatch_id"]
         node_id = task_metadata["node_id"]
         operation_id = f"{dispatch_id}_{node_id}"
@@ -453,6 +582,9 @@ class SSHExecutor(RemoteExecutor):
         names = self._write_function_files(operation_id, function, args, kwargs, workdir)
         function_file, script_file, remote_function_file, remote_script_file, remote_result_file = names
         result_file = _join(self.cache_dir, f"result_{operation_id}.pkl")
+        entry = _inflight.get(function_file)
+        if entry is not None:
+            entry.live_key = (self.hostname, dispatch_id, node_id)
         released = False
         try:
             await self._upload_task(conn, function_file, remote_function_file, script_file,
@@ -471,7 +603,8 @@ class SSHExecutor(RemoteExecutor):
             result, exception = await self.query_result(conn, result_file, remote_result_file)
 
             if not self.do_cleanup and os.environ.get("B2_EMIT_ARTIFACTS", "") == "1":
-                _emit_artifacts(function_file, script_file, result_file, function, args, kwargs,
+                _emit_artifacts(self, function_file, script_file, result_file, remote_function_file,
+                                remote_script_file, remote_result_file, workdir, function, args, kwargs,
                                 result, exception)
             if self.do_cleanup:
                 released = True
@@ -496,6 +629,16 @@ class SSHExecutor(RemoteExecutor):
         return result
 
 
+# The helpers ``run`` awaits, as defined above: the fused body of ``run`` is only taken while
+# every one of them is still the original (tests patch them; subclasses may override them).
+_ORIG = (SSHExecutor._validate_credentials, SSHExecutor._client_connect, SSHExecutor._write_function_files,
+         SSHExecutor._upload_task, SSHExecutor.submit_task, SSHExecutor._poll_task, SSHExecutor.query_result,
+         SSHExecutor.cleanup, SSHExecutor.get_status, SSHExecutor._attempt_client_connect)
+_HELPER_NAMES = frozenset(("_validate_credentials", "_client_connect", "_write_function_files", "_upload_task",
+                           "submit_task", "_poll_task", "query_result", "cleanup", "get_status",
+                           "_attempt_client_connect"))
+
+
 def _unwrap_covalent_call(fn, args, kwargs):
     """Covalent core does not hand the user's function to ``run`` directly: it passes
     ``functools.partial(wrapper_fn, TransportableObject(user_fn), call_before, call_after)``
@@ -517,20 +660,39 @@ def _unwrap_covalent_call(fn, args, kwargs):
     return (plain(bound[0]), [plain(a) for a in args], {k: plain(v) for k, v in kwargs.items()}, wrapper_type)
 
 
-def _emit_artifacts(function_file, script_file, result_file, fn, args, kwargs, result, exception) -> None:
+def _remote_path(path: str) -> str:
+    """Where a "remote" artefact name lands on this machine: relative names are relative to
+    the login directory, as they are for the reference's SSH session."""
+    return path if os.path.isabs(path) else os.path.join(os.environ.get("HOME", "."), path)
+
+
+def _emit_artifacts(executor, function_file, script_file, result_file, remote_function_file,
+                    remote_script_file, remote_result_file, workdir, fn, args, kwargs, result,
+                    exception) -> None:
     """Compatibility mode, opt-in with B2_EMIT_ARTIFACTS=1 and
-    ``do_cleanup=False``: leave the same three local artefacts the reference leaves
-    behind (ssh.py:147-171, 451-456) — same names, same pickle formats — for tooling
-    that inspects ``cache_dir``.  Nothing on the execution path reads them."""
+    ``do_cleanup=False``: leave behind every artefact the reference leaves (ssh.py:147-171,
+    360-361, 451-456) — ``function_<id>.pkl`` (cloudpickle of ``(fn, args, kwargs)``),
+    ``exec_<id>.py`` (the run-script template formatted with the same three fields, so
+    ``python exec_<id>.py`` reproduces the run from the remote-side files) and
+    ``result_<id>.pkl`` (cloudpickle of ``(result, exception)``), under ``cache_dir`` AND under
+    ``remote_cache`` with the reference's names — for tooling that inspects those directories.
+    Nothing on the execution path reads them.  Array results are views of pinned egress
+    memory; pickle protocol 5 writes such buffers to the file without an intermediate copy."""
     import cloudpickle
 
-    os.makedirs(os.path.dirname(function_file) or ".", exist_ok=True)
-    with open(function_file, "wb") as fh:
-        cloudpickle.dump((fn, args, kwargs), fh)
-    with open(script_file, "w", encoding="utf-8") as fh:
-        fh.write("# executed on a B200 by covalent_ssh_plugin_b200 (device callback); no script ran\n")
-    with open(result_file, "wb") as fh:
-        cloudpickle.dump((result, exception), fh)
+    template = (Path(__file__).parent / "exec.py").read_text(encoding="utf-8")
+    script = template.format(remote_result_file=remote_result_file, remote_function_file=remote_function_file,
+                             current_remote_workdir=workdir or ".")
+    for local, remote, payload in ((function_file, remote_function_file, (fn, args, kwargs)),
+                                   (result_file, remote_result_file, (result, exception))):
+        for path in (local, _remote_path(remote)):
+            os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            with open(path, "wb") as fh:
+                cloudpickle.dump(payload, fh)
+    for path in (script_file, _remote_path(remote_script_file)):
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        with open(path, "w", encoding="utf-8") as fh:
+            fh.write(script)
 
 
 def _forget(conn, *names: str) -> None:
@@ -559,7 +721,10 @@ async def _open_engine(ordinal: int, hostname: str) -> DeviceConnection:
     except _b2lib.B2Error as err:
         raise ConnectionRefusedError(f"GPU {ordinal} refused: {err}") from err
     conn = _connections[(ordinal, hostname)] = DeviceConnection(engine, hostname)
+    if hostname in _resolved:          # "localhost" follows LOCAL_RANK and is resolved per call
+        _conn_by_host[hostname] = conn
     return conn
 
 
 _connections: Dict[tuple, DeviceConnection] = {}
+_conn_by_host: Dict[str, DeviceConnection] = {}      # GPU-named hosts only: the fused run() looks here

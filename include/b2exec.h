@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1u
+#define B2_ABI_VERSION 2u
 
 /* ---- error codes -------------------------------------------------------- */
 enum b2_err {
@@ -67,7 +67,8 @@ enum b2_task_status {
   B2_TS_OK = 1,
   B2_TS_OVERFLOW = 2,  /* int64 electron overflowed: host must take the _on_ssh_fail path */
   B2_TS_BAD_FN = 3,    /* fn_id has no callback registered                               */
-  B2_TS_BAD_ARG = 4    /* operand out of arena range / misaligned for the callback        */
+  B2_TS_BAD_ARG = 4,   /* operand out of arena range / misaligned for the callback        */
+  B2_TS_CANCELLED = 5  /* tombstoned before the worker reached it (B2_F_CANCELLED / b2_cancel) */
 };
 
 /* ---- built-in callbacks (the on-device stand-in for exec.py:37) ---------- */
@@ -89,6 +90,7 @@ enum b2_kind {
 /* b2_task.flags */
 #define B2_F_IMM0 0x1u          /* arg0 is an immediate, not an arena offset   */
 #define B2_F_IMM1 0x2u          /* arg1 is an immediate                        */
+#define B2_F_CANCELLED 0x4u     /* tombstone: do not run, report B2_TS_CANCELLED (successors are still released) */
 #define B2_F_ARENA0_SHIFT 8     /* bits 8..11 : arena id of arg0 (0 = local)   */
 #define B2_F_ARENA1_SHIFT 12    /* bits 12..15: arena id of arg1               */
 #define B2_F_ARENAO_SHIFT 16    /* bits 16..19: arena id of out                */
@@ -123,6 +125,35 @@ typedef struct b2_span {
   uint64_t bytes;
 } b2_span;
 
+/* One host->pinned-ingress copy of a batch (b2_stage_copy / b2_submit): the
+ * replacement of writing function_<id>.pkl and SCP-ing it (ssh.py:147-150, 360). */
+typedef struct b2_copy_job {
+  uint64_t src;         /* host virtual address of the operand bytes (caller keeps it alive) */
+  uint64_t dst_off;     /* byte offset inside the pinned ingress buffer                      */
+  uint64_t bytes;
+} b2_copy_job;
+
+/* b2_batch.flags */
+#define B2_BATCH_INDEPENDENT 0x1u  /* no task has deps or successors (plain fan-out): skip the table scan */
+
+/* One whole batch of electrons for b2_submit: everything ssh.py:466-591 does for
+ * ONE electron, for n_tasks of them, in one asynchronous call. */
+typedef struct b2_batch {
+  const b2_copy_job *jobs;   /* operand copies into the pinned ingress buffer (may be NULL)     */
+  const b2_task *tasks;      /* task records; offsets refer to the arena                        */
+  uint32_t n_jobs;
+  uint32_t n_tasks;
+  uint32_t flags;            /* B2_BATCH_*                                                      */
+  uint32_t reserved;
+  uint64_t in_off;           /* ingress range to upload after the copies: host off == arena off */
+  uint64_t in_bytes;
+  uint64_t status_host_off;  /* egress offset receiving n_tasks status words                    */
+  uint64_t out_dev_off;      /* arena range holding the results ...                             */
+  uint64_t out_host_off;     /* ... downloaded to this egress offset                            */
+  uint64_t out_bytes;
+  uint64_t ticket;           /* OUT: completion ticket for b2_poll / b2_wait                    */
+} b2_batch;
+
 typedef struct b2_device_info {
   int32_t  cc_major, cc_minor;
   int32_t  sm_count;
@@ -149,6 +180,10 @@ typedef struct b2_stats {
 /* ---- lifecycle ----------------------------------------------------------- */
 const char *b2_last_error(void);
 int b2_abi_version(void);
+/* First 16 hex digits of the SHA-256 over every file of csrc/, this header and the compiler
+ * flags the library was built from (covalent_ssh_plugin_b200/build.py); "unknown" for a build
+ * that did not pass -DB2_SRC_HASH. */
+const char *b2_source_hash(void);
 int b2_device_count(int *count);
 
 /* Opens the "connection" to one GPU (replaces asyncssh.connect, ssh.py:263-268):
@@ -212,6 +247,25 @@ int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ,
  * uint32 b2_task_status per electron (pass UINT64_MAX to skip the copy).
  * Returns a ticket for b2_poll / b2_wait. */
 int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket);
+/* The whole per-batch pipeline in ONE asynchronous call (replaces, per electron,
+ * ssh.py:147-150 pickle + 360-361 upload + 377-383 run + 451 download): a submission
+ * thread inside the library copies the operands into pinned ingress memory (b2_copy_job,
+ * several host threads, non-temporal stores), uploads [in_off, +in_bytes), runs the
+ * worker over the task records, downloads statuses and results, and records the ticket.
+ * Returns as soon as the batch is queued; batch->ticket is valid on return.  jobs, tasks
+ * and the operand memory must stay valid until the ticket has completed.  Batches run in
+ * submission order; every other stream-ordered call of this ABI first waits until queued
+ * submissions have been issued, so program order is kept.  Do not interleave with an open
+ * b2_enqueue .. b2_launch pair.  A failure inside the pipeline is reported by
+ * b2_poll / b2_wait on the ticket. */
+int b2_submit(int dev, b2_batch *batch);
+/* The host-copy stage alone, synchronously (same thread pool). */
+int b2_stage_copy(int dev, const b2_copy_job *jobs, uint32_t n);
+/* Tombstones electrons [first, first+count) of the batch behind `ticket` (b2_submit or
+ * b2_launch) that the worker has not reached yet: they report B2_TS_CANCELLED instead of
+ * running.  Best effort once the batch is on the device; exact before.  (The reference
+ * cannot cancel at all: ssh.py:460-464.) */
+int b2_cancel(int dev, uint64_t ticket, uint32_t first, uint32_t count);
 /* Records a completion ticket after whatever has been queued so far. */
 int b2_mark(int dev, uint64_t *ticket);
 int b2_poll(int dev, uint64_t ticket);          /* B2_OK | B2_E_NOTREADY  (ssh.py:388-406) */

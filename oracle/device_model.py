@@ -26,8 +26,8 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 K_NONE, K_COPY, K_SCALE_ADD, K_ADD, K_MUL, K_AXPY, K_SUM, K_STACK_SUM, K_IADD, K_IMUL, K_ISCALE_ADD = range(11)
-TS_PENDING, TS_OK, TS_OVERFLOW, TS_BAD_FN, TS_BAD_ARG = 0, 1, 2, 3, 4
-F_IMM0, F_IMM1 = 1, 2
+TS_PENDING, TS_OK, TS_OVERFLOW, TS_BAD_FN, TS_BAD_ARG, TS_CANCELLED = 0, 1, 2, 3, 4, 5
+F_IMM0, F_IMM1, F_CANCELLED = 1, 2, 4
 INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1
 
 
@@ -172,7 +172,10 @@ def run_tasks(arena: np.ndarray, fn_table: dict, tasks: Sequence[dict], succ: Se
         i = ready.pop(0)
         t = tasks[i]
         entry = fn_table.get(int(t["fn_id"]), {"kind": K_NONE})
-        status[i] = run_callback(arena, entry, t, peers)
+        if int(t["flags"]) & F_CANCELLED:      # tombstone: nothing runs, successors are still released
+            status[i] = TS_CANCELLED
+        else:
+            status[i] = run_callback(arena, entry, t, peers)
         for e in range(int(t["succ_count"])):
             j = int(succ[int(t["succ_begin"]) + e])
             deps[j] -= 1

@@ -25,9 +25,9 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", autouse=True)
 def built_library():
-    from covalent_ssh_plugin_b200.build import build_library
+    from covalent_ssh_plugin_b200.build import build_all
 
-    return build_library()
+    return build_all()
 
 
 def _cuda_device_count() -> int:

@@ -73,6 +73,9 @@ class FakeLib:
     def b2_abi_version(self):
         return L.ABI_VERSION
 
+    def b2_source_hash(self):
+        return b"fake-numpy-model"
+
     def b2_device_count(self, ref):
         _deref(ref).value = self.n_devices
         return 0 if self.n_devices else self._fail(L.B2_E_CUDA, "no CUDA-capable device is detected")
@@ -219,6 +222,50 @@ class FakeLib:
                 d.h_out[status_off:status_off + 4 * len(tasks)] = np.array(status, dtype=np.uint32).view(np.uint8)
         return self.b2_mark(dev, tref)
 
+    # -- whole-batch submission (the real library does this on its own thread) ----------
+    def _run_jobs(self, d, jobs, n):
+        if not n:
+            return 0
+        rows = np.frombuffer((C.c_uint8 * (24 * n)).from_address(_addr(jobs)), dtype=L.JOB_DTYPE)
+        self.jobs_run = getattr(self, "jobs_run", 0) + n
+        for r in rows:
+            src, off, nb = int(r["src"]), int(r["dst_off"]), int(r["bytes"])
+            if off + nb > d.h_in.size:
+                return self._fail(L.B2_E_ARG, "copy job outside ingress staging")
+            if nb:
+                d.h_in[off:off + nb] = np.frombuffer((C.c_uint8 * nb).from_address(src), dtype=np.uint8)
+        return 0
+
+    def b2_stage_copy(self, dev, jobs, n):
+        return self._run_jobs(self._dev(dev), jobs, n)
+
+    def b2_submit(self, dev, bref):
+        b = _deref(bref)
+        d = self._dev(dev)
+        self.submits = getattr(self, "submits", 0) + 1
+        rc = self._run_jobs(d, b.jobs, b.n_jobs)
+        if rc == 0 and b.in_bytes:
+            rc = self.b2_h2d(dev, b.in_off, b.in_off, b.in_bytes)
+        if rc == 0 and b.n_tasks:
+            rc = self.b2_enqueue(dev, b.tasks, b.n_tasks, None, 0, None)
+        t = C.c_uint64()
+        if rc == 0:
+            rc = self.b2_launch(dev, b.status_host_off, t)
+        if rc == 0 and b.out_bytes:
+            rc = self.b2_d2h(dev, b.out_dev_off, b.out_host_off, b.out_bytes)
+        if rc != 0:
+            # like the real library: the submission is accepted, the failure surfaces on the ticket
+            d.pending, d.pending_succ = [], []
+            self.b2_mark(dev, t)
+            self._ticket_err = getattr(self, "_ticket_err", {})
+            self._ticket_err[(dev, t.value)] = (rc, self.err)
+        b.ticket = t.value
+        return 0
+
+    def b2_cancel(self, dev, ticket, first, count):
+        self.cancels = getattr(self, "cancels", []) + [(dev, ticket, first, count)]
+        return 0          # the fake runs a batch inside b2_submit: nothing is left to tombstone
+
     def b2_peer_enable(self, dev, peer, aref):
         d = self._dev(dev)
         if peer not in self.devs:
@@ -240,7 +287,17 @@ class FakeLib:
         self._polls[(dev, d.ticket)] = self.delay_polls
         return 0
 
+    def _ticket_failure(self, dev, ticket):
+        err = getattr(self, "_ticket_err", {}).get((dev, ticket))
+        if err is None:
+            return 0
+        self.err = err[1]
+        return err[0]
+
     def b2_poll(self, dev, ticket):
+        rc = self._ticket_failure(dev, ticket)
+        if rc:
+            return rc
         left = self._polls.get((dev, ticket), 0)
         if left > 0:
             self._polls[(dev, ticket)] = left - 1
@@ -248,6 +305,9 @@ class FakeLib:
         return 0
 
     def b2_wait(self, dev, ticket):
+        rc = self._ticket_failure(dev, ticket)
+        if rc:
+            return rc
         self._polls[(dev, ticket)] = 0
         return 0
 

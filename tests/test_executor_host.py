@@ -225,11 +225,13 @@ def test_file_writes():
     assert remote_result_file == os.path.join(executor.remote_cache, f"result_{operation_id}.pkl")
 
 
-def test_cancel_is_unsupported_like_the_reference():
+def test_cancel_with_nothing_in_flight_reports_false():
+    """The reference raises NotImplementedError here (ssh.py:460-464); this executor can
+    cancel (tests below), and with nothing in flight there is nothing to do."""
     with patch(CFG, side_effect=get_config_mock):
         executor = SSHExecutor(username="user", hostname="host", ssh_key_file="key_file")
-    with pytest.raises(NotImplementedError):
-        asyncio.run(executor.cancel())
+    assert asyncio.run(executor.cancel()) is False
+    assert asyncio.run(executor.cancel({"dispatch_id": "d", "node_id": 1})) is False
 
 
 def test_hostname_resolution():
@@ -540,9 +542,10 @@ def test_host_pool_is_opt_in_and_mirrors_exec_py(fake_lib, tmp_path):
 
 
 def test_large_operands_are_staged_by_threads(fake_lib, tmp_path):
-    """Operands above the threshold are copied by the staging threads; a batch is
-    not shipped while copies into it are pending, and results stay correct."""
-    eng = engine_mod.get_engine(0, parallel_stage_bytes=64 << 10, stage_threads=4, **SMALL)
+    """Operands travel as copy jobs (source address, ingress offset, bytes) that the library's
+    copy threads run when the batch is submitted — never inline on the event-loop thread — and
+    results stay correct."""
+    eng = engine_mod.get_engine(0, parallel_stage_bytes=64 << 10, **SMALL)
     ex = make_executor(tmp_path)
     n = 60
     xs = [np.random.default_rng(i).standard_normal(20000 + 31 * i, dtype=np.float32) for i in range(n)]   # ~80 KiB each
@@ -558,30 +561,50 @@ def test_large_operands_are_staged_by_threads(fake_lib, tmp_path):
     for i in range(n):
         assert np.array_equal(out[i], xs[i] * ys[i])
         assert np.array_equal(out[n + i], np.float32(2.0) * small[i] + np.float32(1.0))
-    assert eng._stage_pool is not None
+    assert fake_lib.jobs_run >= n                # (electrons that had to wait for a segment copy small operands inline)
     del out
     assert sorted(eng._free_segments) == [0, 1, 2, 3]
 
 
 def test_artifact_compatibility_mode(fake_lib, tmp_path):
-    """do_cleanup=False + B2_EMIT_ARTIFACTS=1 leaves the reference's three local
-    artefacts (names pinned by the reference's test_file_writes) with its pickle formats."""
+    """do_cleanup=False + B2_EMIT_ARTIFACTS=1 leaves the reference's artefacts — local AND
+    remote-side names (pinned by the reference's test_file_writes), its pickle formats, and a
+    run script formatted from the template exactly as ssh.py:164-169 formats exec.py — and the
+    emitted script really reproduces the result from the remote-side files."""
+    import subprocess
+    import sys
+
     import cloudpickle
 
     engine_mod.get_engine(0, **SMALL)
-    ex = make_executor(tmp_path, do_cleanup=False)
+    cache, remote = tmp_path / "cache", tmp_path / "remote"
+    cache.mkdir()
+    key = tmp_path / "id_stub"
+    key.touch()
+    ex = SSHExecutor(username="u", hostname="cuda:0", ssh_key_file=str(key), cache_dir=str(cache),
+                     remote_cache=str(remote), remote_workdir=str(tmp_path / "work"), do_cleanup=False)
     x = np.arange(64, dtype=np.float32)
     with patch.dict(os.environ, {"B2_EMIT_ARTIFACTS": "1"}):
         y = asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "art", "node_id": 3}))
-    names = sorted(p.name for p in tmp_path.iterdir() if "art_3" in p.name)
-    assert names == ["exec_art_3.py", "function_art_3.pkl", "result_art_3.pkl"]
-    fn, args, kwargs = cloudpickle.load(open(tmp_path / "function_art_3.pkl", "rb"))
+    want = ["exec_art_3.py", "function_art_3.pkl", "result_art_3.pkl"]
+    assert sorted(p.name for p in cache.iterdir()) == want
+    assert sorted(p.name for p in remote.iterdir()) == want
+    fn, args, kwargs = cloudpickle.load(open(cache / "function_art_3.pkl", "rb"))
     assert fn is electrons.scale_add and np.array_equal(args[0], x) and kwargs == {}
-    res, exc = cloudpickle.load(open(tmp_path / "result_art_3.pkl", "rb"))
+    res, exc = cloudpickle.load(open(remote / "result_art_3.pkl", "rb"))
     assert exc is None and np.array_equal(res, y)
+    script = (remote / "exec_art_3.py").read_text()
+    assert str(remote / "result_art_3.pkl") in script and str(remote / "function_art_3.pkl") in script
+    assert str(tmp_path / "work") in script and "{" not in script.split("import os")[1]
+    # the script is the real thing: running it rewrites result_<id>.pkl from function_<id>.pkl
+    (remote / "result_art_3.pkl").unlink()
+    env = dict(os.environ, PYTHONPATH=str(Path(__file__).resolve().parents[1]))
+    assert subprocess.run([sys.executable, str(remote / "exec_art_3.py")], env=env).returncode == 0
+    res2, exc2 = cloudpickle.load(open(remote / "result_art_3.pkl", "rb"))
+    assert exc2 is None and np.array_equal(res2, y) and (tmp_path / "work").is_dir()
     # default: nothing is written
     asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "art", "node_id": 4}))
-    assert not [p for p in tmp_path.iterdir() if "art_4" in p.name]
+    assert not [p for p in list(cache.iterdir()) + list(remote.iterdir()) if "art_4" in p.name]
 
 
 def test_large_elementwise_electrons_are_sliced(fake_lib, tmp_path):
