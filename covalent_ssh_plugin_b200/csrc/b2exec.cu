@@ -122,6 +122,7 @@ struct Device {
   uint32_t pend_tasks = 0, pend_succ = 0, succ_cap = 0;
   uint32_t pend_prefix = 0;      // leading electrons with deps == 0
   bool pend_prefix_open = true;
+  bool pend_external = false;    // the pending batch was opened by b2_enqueue (not by the submission thread)
 
   Staging span_ring[kRing];
   int span_slot = 0;
@@ -421,6 +422,7 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   D->pend_tasks = D->pend_succ = 0;
   D->pend_prefix = 0;
   D->pend_prefix_open = true;
+  D->pend_external = false;
   D->task_slot = D->span_slot = 0;
   D->next_ticket = 1;
   D->n_user_ev = 0;
@@ -806,7 +808,9 @@ static int enqueue_locked(Device *D, const b2_task *tasks, uint32_t n, const uin
 int b2_enqueue(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
                uint32_t *first_index) {
   DEV_ORDERED(D, dev);
-  return enqueue_locked(D, tasks, n, succ, n_succ, first_index, false);
+  int rc = enqueue_locked(D, tasks, n, succ, n_succ, first_index, false);
+  if (rc == B2_OK && D->pend_tasks) D->pend_external = true;
+  return rc;
 }
 
 // ---- tickets ---------------------------------------------------------------
@@ -927,6 +931,7 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   D->pend_tasks = D->pend_succ = 0;
   D->pend_prefix = 0;
   D->pend_prefix_open = true;
+  D->pend_external = false;
   return B2_OK;
 }
 
@@ -945,6 +950,7 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
     D->pend_tasks = D->pend_succ = 0;
     D->pend_prefix = 0;
     D->pend_prefix_open = true;
+    D->pend_external = false;
     return rc;
   }
   if (ticket) *ticket = t;
@@ -1111,7 +1117,7 @@ static void submit_one(Device *D, Submission &sub) {
   {
     std::lock_guard<std::mutex> lk(D->mu);
     cudaSetDevice(D->dev);
-    if (D->pend_tasks != 0) {
+    if (D->pend_tasks != 0) {   // cannot happen: ordered calls drain us first, b2_submit refuses an open batch
       rc = fail(B2_E_STATE, "b2_submit while a b2_enqueue batch is open");
     } else if (b.n_tasks) {
       rc = enqueue_locked(D, b.tasks, b.n_tasks, nullptr, 0, nullptr,
@@ -1205,7 +1211,7 @@ int b2_submit(int dev, b2_batch *batch) {
     if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev);
     if (batch->n_tasks > D->qcap)
       return fail(B2_E_NOMEM, "batch of %u electrons exceeds queue capacity %u", batch->n_tasks, D->qcap);
-    if (D->pend_tasks != 0) return fail(B2_E_STATE, "b2_submit while a b2_enqueue batch is open");
+    if (D->pend_external) return fail(B2_E_STATE, "b2_submit while a b2_enqueue batch is open");
     sub.ticket = alloc_ticket(D, kPhaseQueued);
     D->ticket_ntasks[sub.ticket % kTickets] = batch->n_tasks;
   }

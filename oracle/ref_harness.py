@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE — loads the UNMODIFIED reference plugin and runs it.
 
-Only usable where /root/reference exists (the build container); nothing that
-runs on the GPU box may import this.  It is used to (a) generate the golden
-vectors under tests/golden/ (tests/golden/make_golden.py) and (b) validate the
-restated port in oracle/reference_port.py (tests/test_oracle_vs_reference.py).
+Usable where the reference is present: /root/reference (the build container) or the copy that
+oracle/make_ref.py pip-installed into git-ignored oracle/_ref/ (which travels to the GPU box).
+Nothing on the GPU box reads /root/reference.  It is used to (a) generate the golden
+vectors under tests/golden/ (tests/golden/make_golden.py), (b) validate the
+restated port in oracle/reference_port.py (tests/test_oracle_vs_reference.py) and
+(c) time the reference's own code as the CPU baseline (bench.py, kind "reference").
 
 The reference's two third-party imports that are absent here are stubbed:
 
@@ -33,7 +35,17 @@ import types
 from pathlib import Path
 from typing import Any, Dict, Optional
 
-REFERENCE_ROOT = Path(os.environ.get("B2_REFERENCE_ROOT", "/root/reference"))
+def _reference_root() -> Path:
+    """$B2_REFERENCE_ROOT, else the source tree (build container), else the installed copy."""
+    if os.environ.get("B2_REFERENCE_ROOT"):
+        return Path(os.environ["B2_REFERENCE_ROOT"])
+    for cand in (Path("/root/reference"), Path(__file__).resolve().parent / "_ref"):
+        if (cand / "covalent_ssh_plugin" / "ssh.py").is_file():
+            return cand
+    return Path("/root/reference")
+
+
+REFERENCE_ROOT = _reference_root()
 _PLUGIN_FILE = REFERENCE_ROOT / "covalent_ssh_plugin" / "ssh.py"
 
 _module = None

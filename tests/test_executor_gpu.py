@@ -167,3 +167,31 @@ def test_same_seeded_inputs_through_oracle_port_and_gpu(executor, tmp_path):
             assert abs(float(w) - float(g)) <= 1e-6 * abs(float(w)), fn          # tolerance stated in north_star
         else:
             assert w == g, fn
+
+
+def test_executor_cancel_on_the_gpu(executor, gpu_count, tmp_path):
+    """SSHExecutor.cancel through the whole stack on cuda:0: tombstoned electrons raise
+    TaskCancelledError, their batch-mates return exact results."""
+    if gpu_count < 1:
+        pytest.skip("no CUDA device on this box")
+    from covalent_ssh_plugin_b200 import electrons
+    from covalent_ssh_plugin_b200.ssh import TaskCancelledError
+
+    ex = executor
+    xs = [np.random.default_rng(i).standard_normal(16384, dtype=np.float32) for i in range(200)]
+
+    async def go():
+        await ex.run(electrons.add_int, [1, 1], {}, {"dispatch_id": "warm", "node_id": 0})    # opens the engine
+        tasks = [asyncio.ensure_future(ex.run(electrons.scale_add, [xs[i]], {}, {"dispatch_id": "gc", "node_id": i}))
+                 for i in range(200)]
+        await asyncio.sleep(0)
+        for i in range(0, 200, 7):
+            assert await ex.cancel({"dispatch_id": "gc", "node_id": i})
+        return await asyncio.gather(*tasks, return_exceptions=True)
+
+    out = asyncio.run(go())
+    for i in range(200):
+        if i % 7 == 0:
+            assert isinstance(out[i], TaskCancelledError), i
+        else:
+            assert np.array_equal(out[i], np.float32(2.0) * xs[i] + np.float32(1.0)), i
