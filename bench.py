@@ -366,7 +366,7 @@ def run_cuda_arm(args, dist: Dist):
     n_seg = max(n_seg, -(-(n * ((payload + 255) & ~255) + (1 << 20)) // per_seg) + 1)
     n_out = max(n_out, n_seg)
     staging = n_seg * per_seg
-    heap = 2 * total + 768 * MiB
+    heap = max(2 * total + 768 * MiB, 2 * GiB + 256 * MiB)      # the C5 cells use 2 x 1 GiB of it
     arena = staging + n_out * per_seg + (1 << 20) + heap
     eng = get_engine(dev, arena_bytes=arena, staging_bytes=staging, n_segments=n_seg, n_out_segments=n_out,
                      max_batch=max_batch, queue_cap=1 << 16)
@@ -519,6 +519,10 @@ def run_cuda_arm(args, dist: Dist):
     d2h = (c1["bytes_out"] - c0["bytes_out"]) // e2e_steps + 4 * len(mine)
     e2e_launches = int((st1.launches_worker - st0.launches_worker) + (st1.launches_pack - st0.launches_pack))
     value = n / e2e_s
+    if rank == 0:
+        print(f"[bench] worker_step {ms_dev_max:.4f} ms ({worker_gbs / peak:.3f} of peak), pack {kernels['pack']['frac']:.3f}, "
+              f"unpack {kernels['unpack']['frac']:.3f}; lattice through run(): {value / 1e3:.1f} k electrons/s "
+              f"({1e3 * e2e_s:.1f} ms/step, verified={verified})", file=sys.stderr, flush=True)
 
     clk = clocks.stop() if clocks else None
 
