@@ -354,19 +354,21 @@ def run_cuda_arm(args, dist: Dist):
     from covalent_ssh_plugin_b200.engine import get_engine, shutdown_all
 
     dev, world, rank = dist.local_rank, dist.world, dist.rank
-    if (world > 1 and os.environ.get("B2_BENCH_BIND", "1") != "0") or os.environ.get("B2_BENCH_BIND") == "1":
-        bind_to_gpu_numa(dev)
+    all_cpus = os.sched_getaffinity(0)
+    if os.environ.get("B2_BENCH_BIND", "1") != "0":
+        bind_to_gpu_numa(dev)          # dispatcher + copy threads next to their GPU; undone before the CPU baseline
     n, payload = args.electrons, args.payload
     count = payload // 4
     total = n * payload
     max_batch = env_int("B2_MAX_BATCH", 1024)
-    dev_batch = 4096                                      # worker_step launches (device-resident loop)
+    dev_batch = min(n, 1 << 16)     # device-resident operands need no staging pipeline: one launch per step,
+                                    # as engine.run_dag / a lattice level issues it (queue capacity 65 536)
     per_seg, n_seg, n_out = engine_shape(n, payload, max_batch)
     # the ingress mirror must also hold the whole device-resident input set of worker_step
     n_seg = max(n_seg, -(-(n * ((payload + 255) & ~255) + (1 << 20)) // per_seg) + 1)
     n_out = max(n_out, n_seg)
     staging = n_seg * per_seg
-    heap = max(2 * total + 768 * MiB, 2 * GiB + 256 * MiB)      # the C5 cells use 2 x 1 GiB of it
+    heap = max(2 * total + 768 * MiB, 8 * GiB + 256 * MiB)      # the C5 cells use 2 x 4 GiB of it
     arena = staging + n_out * per_seg + (1 << 20) + heap
     eng = get_engine(dev, arena_bytes=arena, staging_bytes=staging, n_segments=n_seg, n_out_segments=n_out,
                      max_batch=max_batch, queue_cap=1 << 16)
@@ -444,13 +446,41 @@ def run_cuda_arm(args, dist: Dist):
         traffic_src = f"profiles/traffic.json ({tj.get('captured_on', 'ncu --set full capture')})"
     except Exception:
         pass
-    kernels = {"worker_step": {
+    # the same step from a RESIDENT table (b2_table_launch): no table rebuild / pinned copy / upload per launch
+    tids = []
+    for tab in tabs:
+        tid = C.c_uint32()
+        L.call("b2_table_create", dev, tab.ctypes.data, len(tab), None, 0, C.byref(tid))
+        tids.append(tid.value)
+
+    def resident_step():
+        for tid in tids:
+            L.call("b2_table_launch", dev, tid, L.NO_STATUS_COPY, C.byref(ticket))
+
+    L.call("b2_fill", dev, out0, 0, n * slot)
+    resident_step()
+    L.call("b2_read", dev, out0 + (n - 1) * slot, got.ctypes.data, payload)
+    assert np.array_equal(got, np.float32(2.0) * blk[(n - 1) * count:] + np.float32(1.0)), \
+        "resident-table step result differs from numpy"
+    for _ in range(3):
+        resident_step()
+    dist.barrier()
+    ms_res = dist.max(timed(resident_step, dev_steps))
+    dist.barrier()
+    for tid in tids:
+        L.call("b2_table_destroy", dev, tid)
+    res_gbs = (2.0 * total / 1e9) / (ms_res / 1e3)
+    kernels = {"worker_resident": {
+        "what": "the same step launched from a resident task table (b2_table_launch): no per-launch table work on the host",
+        "ms_per_step": ms_res, "steps": dev_steps, "achieved_gbs": res_gbs, "frac": res_gbs / peak,
+        "electrons_per_s_per_gpu": n / (ms_res / 1e3)}}
+    kernels["worker_step"] = {
         "what": "device-resident step: per step %d x (b2_enqueue + table upload + worker_tma_kernel launch) over "
                 "%d electrons already in HBM" % (len(tabs), n),
         "electrons_per_s_per_gpu": n / (ms_dev_max / 1e3), "ms_per_step": ms_dev_max, "steps": dev_steps,
         "ms_per_rank": {"min": min(ms_ranks), "median": statistics.median(ms_ranks), "max": ms_dev_max},
         "achieved_gbs": worker_gbs, "frac": worker_gbs / peak,
-        "algorithmic_bytes_per_launch": 2.0 * total / len(tabs), "launches_per_step": len(tabs)}}
+        "algorithmic_bytes_per_launch": 2.0 * total / len(tabs), "launches_per_step": len(tabs)}
 
     # ============ kernels.pack / unpack on the same payload set (rank-local) ======================
     heap0 = eng.heap_base
@@ -520,7 +550,7 @@ def run_cuda_arm(args, dist: Dist):
     e2e_launches = int((st1.launches_worker - st0.launches_worker) + (st1.launches_pack - st0.launches_pack))
     value = n / e2e_s
     if rank == 0:
-        print(f"[bench] worker_step {ms_dev_max:.4f} ms ({worker_gbs / peak:.3f} of peak), pack {kernels['pack']['frac']:.3f}, "
+        print(f"[bench] worker_step {ms_dev_max:.4f} ms ({worker_gbs / peak:.3f} of peak; resident table {res_gbs / peak:.3f}), pack {kernels['pack']['frac']:.3f}, "
               f"unpack {kernels['unpack']['frac']:.3f}; lattice through run(): {value / 1e3:.1f} k electrons/s "
               f"({1e3 * e2e_s:.1f} ms/step, verified={verified})", file=sys.stderr, flush=True)
 
@@ -534,7 +564,7 @@ def run_cuda_arm(args, dist: Dist):
             sp, sn_seg, sn_out = engine_shape(-(-n // world), payload, max_batch)
             exs = [ex]
             for d in range(1, world):
-                get_engine(d, arena_bytes=sn_seg * sp + sn_out * sp + 256 * MiB, staging_bytes=sn_seg * sp,
+                get_engine(d, arena_bytes=sn_seg * sp + sn_out * sp + 3 * GiB, staging_bytes=sn_seg * sp,
                            n_segments=sn_seg, n_out_segments=sn_out, max_batch=max_batch, queue_cap=1 << 16)
                 exs.append(SSHExecutor(username="bench", hostname=f"cuda:{d}", ssh_key_file=str(key), cache_dir=tmp))
             xall = [np.random.default_rng([1, i]).standard_normal(count, dtype=np.float32) for i in range(n)]
@@ -625,18 +655,24 @@ def run_cuda_arm(args, dist: Dist):
                 "of_nominal_900": gbs / 900.0, "payloads": m, "payload_bytes": payload, "verified": peer_ok}
         # shared operand: uploaded on rank 0, ncclBroadcast arena -> arena, used as an electron argument
         shared = np.random.default_rng(11).standard_normal(64 * MiB // 4, dtype=np.float32) if rank == 0 else None
+        warm = D.broadcast_shared(eng, shared[:1 << 18] if rank == 0 else None, root=0)   # NCCL setup, not timed
+        warm.free()
         dist.barrier()
+        bstats = {}
         t0 = time.perf_counter()
-        da = D.broadcast_shared(eng, shared, root=0)
+        da = D.broadcast_shared(eng, shared, root=0, stats=bstats)
         dist.barrier()
         dt_b = dist.max(time.perf_counter() - t0)
+        dt_coll = dist.max(bstats.get("collective_seconds", 0.0))
         mine_x = np.random.default_rng([12, rank]).standard_normal(64 * MiB // 4, dtype=np.float32)
         got = asyncio.run(ex.run(electrons.vec_add, [da, mine_x], {}, {"dispatch_id": "bc", "node_id": rank}))
         ref = np.random.default_rng(11).standard_normal(64 * MiB // 4, dtype=np.float32) + mine_x
         bcast = {"bytes": 64 * MiB, "seconds": dt_b, "gbs": 64 * MiB / 1e9 / dt_b,
+                 "collective_seconds": dt_coll, "collective_gbs": (64 * MiB / 1e9 / dt_coll) if dt_coll else None,
                  "exact": dist.all_true(bool(np.array_equal(got, ref))),
-                 "what": "one 64 MiB operand uploaded on rank 0, ncclBroadcast arena->arena, then used by a vec_add "
-                         "electron on every rank (time includes the upload and the collective's first-call setup)"}
+                 "what": "one 64 MiB operand uploaded on rank 0 (pageable host memory), ncclBroadcast arena->arena, "
+                         "then used by a vec_add electron on every rank; `seconds` = upload + collective, "
+                         "`collective_seconds` = the ncclBroadcast alone (max over ranks)"}
         da.free()
         del got, ref, mine_x
 
@@ -652,6 +688,7 @@ def run_cuda_arm(args, dist: Dist):
     # ============ CPU baseline (rank 0, N = 1 only) =================================================
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)          # the reference gets every host core
         cores = len(os.sched_getaffinity(0))
         base = reference_cpu_sample(max(32, min(128, cores)), payload, passes=3)
         cpu = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "per_pass")}
@@ -700,12 +737,14 @@ def run_cuda_arm(args, dist: Dist):
 
 def sweep_c5(L, eng, ex, electrons, spec, timed, peak, dev, heap0, heap_used):
     """BASELINE config 5 on one GPU: per payload size the worker kernel on device-resident operands
-    (GB/s against the HBM copy peak) and the end-to-end rate through SSHExecutor.run."""
+    (GB/s against the HBM copy peak; launched from a resident task table, so that the number is the
+    kernel's and not the host's table preparation — `launch_path_gbs` is the b2_enqueue + upload +
+    launch path beside it) and the end-to-end rate through SSHExecutor.run."""
     rows = []
     src0 = heap0
-    budget = 1 * GiB                                     # bytes of operands per cell (in) + same (out)
+    budget = eng.heap_bytes // 2 - 32 * MiB             # operand bytes per cell (in), same again for results
+    budget = min(budget, 4 * GiB) & ~(64 * MiB - 1)
     dst0 = heap0 + budget
-    assert eng.heap_bytes >= 2 * budget + 64 * MiB, "arena heap too small for the C5 cells"
     noise = np.random.default_rng(0).standard_normal(16 * MiB, dtype=np.float32)        # 64 MiB
     L.call("b2_write", dev, src0, noise.ctypes.data, noise.nbytes)
     reps_fill = budget // noise.nbytes
@@ -717,25 +756,40 @@ def sweep_c5(L, eng, ex, electrons, spec, timed, peak, dev, heap0, heap_used):
     L.call("b2_sync", dev)
     ticket = C.c_uint64()
     qcap = 1 << 16
+    slice_bytes = 1 * MiB                                # engine._append slices elementwise electrons >= 2 MiB
     for P in (1 * KiB, 4 * KiB, 16 * KiB, 64 * KiB, 256 * KiB, 1 * MiB, 4 * MiB, 16 * MiB):
         slot = (P + 255) & ~255
         N = int(min(100000, budget // slot))
+        per = P if P < 2 * slice_bytes else slice_bytes
+        parts = P // per
+        n_tasks = N * parts
         tabs = []
-        for lo in range(0, N, qcap):
-            k = min(qcap, N - lo)
+        for lo in range(0, n_tasks, qcap):
+            k = min(qcap, n_tasks - lo)
+            idx = lo + np.arange(k, dtype=np.uint64)
             tab = np.zeros(k, dtype=L.TASK_DTYPE)
             tab["fn_id"] = spec.fn_id
-            tab["arg0"] = src0 + (lo + np.arange(k, dtype=np.uint64)) * slot
-            tab["out"] = dst0 + (lo + np.arange(k, dtype=np.uint64)) * slot
-            tab["count"] = P // 4
+            tab["arg0"] = src0 + (idx // parts) * slot + (idx % parts) * per
+            tab["out"] = dst0 + (idx // parts) * slot + (idx % parts) * per
+            tab["count"] = per // 4
             tabs.append(tab)
 
-        def one_pass():
+        def launch_path():
             for tab in tabs:
                 L.call("b2_enqueue", dev, tab.ctypes.data, len(tab), None, 0, None)
                 L.call("b2_launch", dev, L.NO_STATUS_COPY, C.byref(ticket))
 
-        one_pass()
+        tids = []
+        for tab in tabs:
+            tid = C.c_uint32()
+            L.call("b2_table_create", dev, tab.ctypes.data, len(tab), None, 0, C.byref(tid))
+            tids.append(tid.value)
+
+        def resident():
+            for tid in tids:
+                L.call("b2_table_launch", dev, tid, L.NO_STATUS_COPY, C.byref(ticket))
+
+        resident()
         got = np.empty(P // 4, dtype=np.float32)
         L.call("b2_read", dev, dst0 + (N - 1) * slot, got.ctypes.data, P)
         off = ((N - 1) * slot) % noise.nbytes
@@ -743,11 +797,17 @@ def sweep_c5(L, eng, ex, electrons, spec, timed, peak, dev, heap0, heap_used):
         if off + P <= noise.nbytes:
             exact = bool(np.array_equal(got, np.float32(2.0) * noise.view(np.uint8)[off:off + P].view(np.float32)
                                         + np.float32(1.0)))
-        one_pass()
-        ms = timed(one_pass, 10)
+        resident()
+        ms = timed(resident, 10)
+        launch_path()
+        ms_lp = timed(launch_path, 10)
+        for tid in tids:
+            L.call("b2_table_destroy", dev, tid)
         gbs = 2.0 * N * P / 1e9 / (ms / 1e3)
-        row = {"payload_bytes": P, "electrons": N, "worker_gbs": gbs, "worker_frac": gbs / peak,
-               "worker_electrons_per_s": N / (ms / 1e3), "exact": exact}
+        row = {"payload_bytes": P, "electrons": N, "task_records": n_tasks, "worker_gbs": gbs, "worker_frac": gbs / peak,
+               "worker_electrons_per_s": N / (ms / 1e3), "exact": exact,
+               "launch_path_gbs": 2.0 * N * P / 1e9 / (ms_lp / 1e3),
+               "launch_path_frac": 2.0 * N * P / 1e9 / (ms_lp / 1e3) / peak}
         # end to end: bounded by the staging pool of this bench's engine
         n_e2e = int(min(10000, (256 * MiB) // max(P, 1), eng.max_batch * 3 if P > 256 * KiB else 10000))
         if P <= eng.seg_bytes // 2 and n_e2e >= 8:
@@ -768,7 +828,8 @@ def sweep_c5(L, eng, ex, electrons, spec, timed, peak, dev, heap0, heap_used):
             row.update(e2e_electrons=n_e2e, e2e_electrons_per_s=n_e2e / dt, e2e_gbs_in_plus_out=2.0 * n_e2e * P / dt / 1e9)
         rows.append(row)
     return {"workload": "C5: payload sweep, one GPU, scale_add electrons; worker on device-resident operands "
-                        "(1 GiB of payloads per cell, at most 100 000 electrons), e2e through SSHExecutor.run",
+                        f"({budget // MiB} MiB of payloads per cell, at most 100 000 electrons; electrons >= 2 MiB go out as "
+                        "1 MiB task records, as the engine slices them), e2e through SSHExecutor.run",
             "rows": rows}
 
 
@@ -803,8 +864,11 @@ def diamond_c4(world: int, key, tmp):
         t0 = time.perf_counter()
         r = ct.get_result(ct.dispatch(wf)(x0, ws))
         times.append(time.perf_counter() - t0)
-        exact = exact and r.status == ct.status.COMPLETED and bool(np.array_equal(r.result, want))
+        ok = r.status == ct.status.COMPLETED and bool(np.array_equal(r.result, want))
+        exact = exact and ok
         stats = {k: v for k, v in r.stats.items() if isinstance(v, (int, float, str))}
+        if not ok:
+            stats["error"] = repr(getattr(r, "error", None))[:300]
     return {"workload": f"C4: 1 000-node diamond (root -> 998 x vec_mul -> stack_sum), 1 MiB fp32 operands, fan-out "
                         f"round-robin over {world} GPU(s) of one process",
             "ms": 1e3 * min(times[1:]) if len(times) > 1 else 1e3 * times[0], "ms_first": 1e3 * times[0],

@@ -163,6 +163,9 @@ _SIGNATURES = {
     "b2_submit": ([C.c_int, C.POINTER(Batch)], True),
     "b2_stage_copy": ([C.c_int, C.c_void_p, C.c_uint32], True),
     "b2_cancel": ([C.c_int, C.c_uint64, C.c_uint32, C.c_uint32], True),
+    "b2_table_create": ([C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _u32p], True),
+    "b2_table_launch": ([C.c_int, C.c_uint32, C.c_uint64, _u64p], True),
+    "b2_table_destroy": ([C.c_int, C.c_uint32], True),
     "b2_mark": ([C.c_int, _u64p], True),
     "b2_poll": ([C.c_int, C.c_uint64], False),
     "b2_wait": ([C.c_int, C.c_uint64], True),

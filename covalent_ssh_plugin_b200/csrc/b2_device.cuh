@@ -133,6 +133,8 @@ struct WorkerArgs {
   uint32_t *exited;              // CTAs that have left; the last one re-arms the counters
   uint32_t n_tasks;
   uint32_t n_ready_prefix;       // tasks [0, P) are ready at submit: ticket t < P runs task t
+  uint32_t claim_k;              // tickets a CTA takes per fetch-add on the head (>= 1; streaming worker)
+  uint32_t pad0;
   uint8_t *arena[B2_MAX_ARENAS];
   uint64_t arena_bytes[B2_MAX_ARENAS];
 };

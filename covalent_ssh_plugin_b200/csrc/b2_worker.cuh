@@ -33,8 +33,9 @@ __device__ __forceinline__ void queue_push_warp(const Queue &q, uint32_t first_t
 
 constexpr uint32_t kNoTask = 0xFFFFFFFFu;
 
-// One thread per CTA: claim the next ticket.
+// One thread per CTA: claim the next ticket (or the next n tickets: returns the first).
 __device__ __forceinline__ uint32_t queue_claim(const Queue &q) { return atomicAdd(q.head, 1u); }
+__device__ __forceinline__ uint32_t queue_claim_n(const Queue &q, uint32_t n) { return atomicAdd(q.head, n); }
 
 // One thread per CTA: wait until the claimed ticket has been published.
 __device__ __forceinline__ uint32_t queue_take(const Queue &q, uint32_t ticket, uint32_t n_tasks) {

@@ -35,6 +35,20 @@ namespace b2 {
 constexpr int kStages = B2_TMA_STAGES;
 constexpr uint32_t kTileBytes = B2_TMA_TILE;          // one stage; binary electrons use two halves
 constexpr uint32_t kWorkerSmemBytes = kStages * kTileBytes;
+// Small-payload flavour: same shared-memory budget cut into more, smaller stages.  An electron of
+// a few KiB occupies one stage whatever the stage size, so with 3 x 16 KiB stages a CTA has at
+// most 3 small electrons (a few KiB) in flight — far below what HBM latency needs; 12 x 4 KiB
+// stages keep 12 of them in flight per CTA (48 per SM).  Chosen by the host per launch from the
+// average operand size (b2exec.cu); larger electrons are still correct there, tile by tile.
+#ifndef B2_TMA_SMALL_STAGES
+#define B2_TMA_SMALL_STAGES 12
+#endif
+#ifndef B2_TMA_SMALL_TILE
+#define B2_TMA_SMALL_TILE 4096
+#endif
+constexpr int kSmallStages = B2_TMA_SMALL_STAGES;
+constexpr uint32_t kSmallTileBytes = B2_TMA_SMALL_TILE;
+constexpr uint32_t kWorkerSmallSmemBytes = kSmallStages * kSmallTileBytes;
 constexpr uint32_t kHdrExit = 0xFFFFFFFFu;
 constexpr uint32_t kHdrLegacy = 0xFFFFFFFEu;
 constexpr uint32_t kHdrFailed = 0xFFFFFFFDu;          // status already decided by the producer
@@ -61,8 +75,8 @@ __device__ __forceinline__ bool is_streaming_kind(uint32_t k) {
   return k == B2_K_COPY || k == B2_K_SCALE_ADD || k == B2_K_ADD || k == B2_K_MUL || k == B2_K_AXPY;
 }
 
-__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
-    worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
+template <int kStages, uint32_t kTileBytes>
+__device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
   extern __shared__ __align__(128) uint8_t stage_mem[];   // kStages x kTileBytes, dynamic
   __shared__ StageHdr hdr[kStages];
   __shared__ Slot legacy[kStages];
@@ -98,7 +112,20 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
       // and — when that ticket lies in the ready prefix — its task record is already on its
       // way into registers: the fetch-add and the record's L2 round trips overlap the tile
       // issue of the current electron instead of sitting between two electrons.
-      uint32_t ticket = queue_claim(a.q);
+      // Tickets are claimed a.claim_k at a time (one fetch-add on the shared head per K electrons:
+      // with electrons of a few KiB the single-address atomic is otherwise the rate limiter).  A CTA
+      // runs its tickets in increasing order, so a ticket that has to wait for its cell never sits
+      // in front of a published one: cells are published in ticket order.
+      const uint32_t K = a.claim_k ? a.claim_k : 1u;
+      uint32_t claimed_end = 0;            // one past the last ticket of the current claim
+      auto next_ticket = [&](uint32_t after) -> uint32_t {
+        if (after + 1 < claimed_end) return after + 1;
+        const uint32_t base = queue_claim_n(a.q, K);
+        claimed_end = base + K;
+        return base;
+      };
+      uint32_t ticket = queue_claim_n(a.q, K);
+      claimed_end = ticket + K;
       b2_task t_next = {};
       if (ticket < P) t_next = a.tasks[ticket];
       for (;;) {
@@ -121,7 +148,7 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
           mbar_arrive(smem_addr(&full_bar[s]));
           break;
         }
-        ticket = queue_claim(a.q);
+        ticket = next_ticket(cur);
         if (ticket < P) t_next = a.tasks[ticket];
         uint32_t kind = B2_K__COUNT;
         FnEntry fn;
@@ -364,6 +391,16 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
       __threadfence();
     }
   }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
+    worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
+  worker_tma_body<kStages, kTileBytes>(a);
+}
+
+__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
+    worker_tma_small_kernel(const __grid_constant__ WorkerArgs a) {
+  worker_tma_body<kSmallStages, kSmallTileBytes>(a);
 }
 
 }  // namespace b2

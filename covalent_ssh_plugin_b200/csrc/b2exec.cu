@@ -123,11 +123,26 @@ struct Device {
   uint32_t pend_prefix = 0;      // leading electrons with deps == 0
   bool pend_prefix_open = true;
   bool pend_external = false;    // the pending batch was opened by b2_enqueue (not by the submission thread)
+  uint64_t pend_bytes = 0;       // operand bytes of the pending batch (picks the worker flavour at launch)
+  uint8_t h_fn_kind[B2_MAX_FN] = {};   // host mirror of the callback kinds (b2_register)
 
   Staging span_ring[kRing];
   int span_slot = 0;
 
   int worker_ctas_per_sm = 0;
+  int worker_small_ctas_per_sm = 0;
+  int worker_small_mode = -1;    // B2_WORKER_SMALL: -1 auto (by average operand size), 0 never, 1 always
+  int claim_k_override = 0;      // B2_CLAIM_K
+  struct Table {                 // resident task table (b2_table_create)
+    uint8_t *d_pristine = nullptr;   // [n tasks][n_succ successor indices] as uploaded
+    uint8_t *d_work = nullptr;       // working copy of the tasks (dependency counters are consumed)
+    uint32_t *d_status = nullptr;
+    uint32_t n = 0, n_succ = 0, prefix = 0;
+    uint64_t bytes = 0;
+    bool has_deps = false;
+    bool live = false;
+  };
+  std::vector<Table> tables;
   int mover_ctas_per_sm = 0;
   int mover_unroll = 8;
   bool mover_tma = true;         // bulk-copy-engine kernel for 16 B aligned spans (B2_MOVER=ldg|wide to disable)
@@ -436,6 +451,15 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
     CU(cudaFuncSetAttribute(worker_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kWorkerSmemBytes));
   }
+  CU(cudaFuncSetAttribute(worker_tma_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CU(cudaFuncSetAttribute(worker_tma_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)kWorkerSmallSmemBytes));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_small_ctas_per_sm, worker_tma_small_kernel,
+                                                   kCtaThreads, kWorkerSmallSmemBytes));
+  D->worker_small_mode = env_int("B2_WORKER_SMALL", -1);
+  D->claim_k_override = env_int("B2_CLAIM_K", 0);
+  memset(D->h_fn_kind, 0, sizeof D->h_fn_kind);
+  D->pend_bytes = 0;
   if (D->worker_tma)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_ctas_per_sm, worker_tma_kernel,
                                                      kCtaThreads, kWorkerSmemBytes));
@@ -468,6 +492,7 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   }
   const int wcap = env_int("B2_WORKER_CTAS_PER_SM", 0);
   if (wcap > 0) D->worker_ctas_per_sm = std::min(D->worker_ctas_per_sm, wcap);
+  if (wcap > 0) D->worker_small_ctas_per_sm = std::min(D->worker_small_ctas_per_sm, wcap);
   const int mcap = env_int("B2_MOVER_CTAS_PER_SM", 0);
   if (mcap > 0) D->mover_ctas_per_sm = std::min(D->mover_ctas_per_sm, mcap);
 
@@ -529,6 +554,12 @@ int b2_shutdown(int dev) {
     if (D->arena_ipc[i] && D->arena[i]) cudaIpcCloseMemHandle(D->arena[i]);
   for (auto &s : D->task_ring) staging_free(s);
   for (auto &s : D->span_ring) staging_free(s);
+  for (auto &t : D->tables) {
+    if (t.d_pristine) cudaFree(t.d_pristine);
+    if (t.d_work) cudaFree(t.d_work);
+    if (t.d_status) cudaFree(t.d_status);
+  }
+  D->tables.clear();
   for (auto &e : D->tickets)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   for (uint32_t i = 0; i < D->n_user_ev; ++i)
@@ -747,6 +778,7 @@ int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta, in
   // host copy alive for the duration.
   CU(cudaMemcpyAsync(D->d_fn + fn_id, &e, sizeof e, cudaMemcpyHostToDevice, D->stream));
   CU(cudaStreamSynchronize(D->stream));
+  D->h_fn_kind[fn_id] = (uint8_t)kind;
   return B2_OK;
 }
 
@@ -778,8 +810,10 @@ static int enqueue_locked(Device *D, const b2_task *tasks, uint32_t n, const uin
   } else {
     bool open = D->pend_prefix_open;
     uint32_t prefix = D->pend_prefix;
+    uint64_t bytes = 0;
     for (uint32_t i = 0; i < n; ++i) {
       b2_task t = tasks[i];
+      bytes += (t.fn_id < B2_MAX_FN && D->h_fn_kind[t.fn_id] == B2_K_COPY) ? t.count : t.count * 4;
       if (t.succ_count) {
         if ((uint64_t)t.succ_begin + t.succ_count > n_succ)
           return fail(B2_E_ARG, "task %u: successor range [%u, +%u) outside succ[%u]", i,
@@ -797,6 +831,7 @@ static int enqueue_locked(Device *D, const b2_task *tasks, uint32_t n, const uin
     }
     D->pend_prefix_open = open;
     D->pend_prefix = prefix;
+    D->pend_bytes += bytes;
   }
   if (n_succ)
     memcpy(reinterpret_cast<uint32_t *>(s.h + succ_off) + D->pend_succ, succ, (size_t)n_succ * 4);
@@ -853,6 +888,57 @@ static int record_ticket(Device *D, uint64_t *ticket) {
   return B2_OK;
 }
 
+// Launches the worker over a task table that is already (or will be, in stream order) on the
+// device.  Picks the streaming flavour from the average operand size: electrons of a few KiB run
+// on the 12 x 4 KiB-stage kernel and claim several tickets per fetch-add.
+static int launch_worker(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32_t *d_status,
+                         uint32_t n, uint32_t prefix, uint64_t operand_bytes) {
+  WorkerArgs a;
+  memset(&a, 0, sizeof a);
+  a.tasks = d_tasks;
+  a.succ = d_succ;
+  // status words live in the slot's own device buffer: the copy of batch k's statuses runs on
+  // the egress stream while kernel k+1 (another slot) is already writing its own
+  a.status = d_status;
+  a.fn_table = D->d_fn;
+  a.q.cells = D->d_cells;
+  a.q.head = D->d_head;
+  a.q.tail = D->d_tail;
+  if (++D->epoch == 0) D->epoch = 1;
+  a.q.epoch = D->epoch;
+  a.q.mask = D->qcap - 1;
+  a.cursor = D->d_cursor;
+  a.exited = D->d_exited;
+  a.n_tasks = n;
+  a.n_ready_prefix = prefix;
+  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
+    a.arena[i] = D->arena[i];
+    a.arena_bytes[i] = D->arena_bytes[i];
+  }
+  const uint64_t avg = n ? operand_bytes / n : 0;
+  bool small = D->worker_tma && operand_bytes && avg <= 8192;
+  if (D->worker_small_mode == 0) small = false;
+  if (D->worker_small_mode == 1) small = D->worker_tma;
+  const int per_sm = small ? D->worker_small_ctas_per_sm : D->worker_ctas_per_sm;
+  const int cap = D->sm_count * std::max(1, per_sm);
+  const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
+  uint32_t k = 1;
+  if (operand_bytes) k = avg <= 2048 ? 8u : avg <= 8192 ? 4u : avg <= 32768 ? 2u : 1u;
+  while (k > 1 && (uint64_t)grid * k * 4 > n) k >>= 1;   // keep >= 4 claims per CTA: the tail stays short
+  if (D->claim_k_override > 0) k = (uint32_t)D->claim_k_override;
+  a.claim_k = k;
+  if (!D->worker_tma)
+    worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
+  else if (small)
+    worker_tma_small_kernel<<<grid, kCtaThreads, kWorkerSmallSmemBytes, D->stream>>>(a);
+  else
+    worker_tma_kernel<<<grid, kCtaThreads, kWorkerSmemBytes, D->stream>>>(a);
+  CU(cudaGetLastError());
+  D->stats.launches_worker += 1;
+  D->stats.electrons += n;
+  return B2_OK;
+}
+
 // Uploads the pending batch's table, launches the worker over it and queues the status copy.
 // `t` (0 = none) is the ticket that will cover this launch: its slot is remembered for
 // b2_cancel.  Caller holds the device lock and records the ticket afterwards.
@@ -875,42 +961,17 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   CU(cudaEventRecord(s.up, D->upload));
   CU(cudaStreamWaitEvent(D->stream, s.up, 0));
 
-  WorkerArgs a;
-  memset(&a, 0, sizeof a);
-  a.tasks = reinterpret_cast<b2_task *>(s.d);
-  a.succ = reinterpret_cast<const uint32_t *>(s.d + succ_off);
-  // status words live in the slot's own device buffer: the copy of batch k's statuses runs on
-  // the egress stream while kernel k+1 (another slot) is already writing its own
   uint32_t *slot_status = reinterpret_cast<uint32_t *>(s.d + succ_off + (size_t)D->succ_cap * 4);
-  a.status = slot_status;
-  a.fn_table = D->d_fn;
-  a.q.cells = D->d_cells;
-  a.q.head = D->d_head;
-  a.q.tail = D->d_tail;
-  if (++D->epoch == 0) D->epoch = 1;
-  a.q.epoch = D->epoch;
-  a.q.mask = D->qcap - 1;
-  a.cursor = D->d_cursor;
-  a.exited = D->d_exited;
-  a.n_tasks = n;
-  a.n_ready_prefix = D->pend_prefix;
-  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
-    a.arena[i] = D->arena[i];
-    a.arena_bytes[i] = D->arena_bytes[i];
+  {
+    int rc_ = launch_worker(D, reinterpret_cast<b2_task *>(s.d), reinterpret_cast<const uint32_t *>(s.d + succ_off),
+                            slot_status, n, D->pend_prefix, D->pend_bytes);
+    if (rc_) return rc_;
   }
-  const int cap = D->sm_count * std::max(1, D->worker_ctas_per_sm);
-  const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
-  if (D->worker_tma)
-    worker_tma_kernel<<<grid, kCtaThreads, kWorkerSmemBytes, D->stream>>>(a);
-  else
-    worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
   CU(cudaGetLastError());
   // the slot (pinned table + device mirror + status words) is reusable once this kernel — and the
   // status copy below, if any — is done
   if (status_host_off == UINT64_MAX) CU(cudaEventRecord(s.ev, D->stream));
   s.in_flight = true;
-  D->stats.launches_worker += 1;
-  D->stats.electrons += n;
   if (status_host_off != UINT64_MAX) {
     int rc_ = egress_after_compute(D);
     if (rc_) return rc_;
@@ -932,6 +993,7 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   D->pend_prefix = 0;
   D->pend_prefix_open = true;
   D->pend_external = false;
+  D->pend_bytes = 0;
   return B2_OK;
 }
 
@@ -954,6 +1016,110 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
     return rc;
   }
   if (ticket) *ticket = t;
+  return B2_OK;
+}
+
+// ---- resident task tables ------------------------------------------------------
+// A lattice that is dispatched again and again (same graph, same arena offsets) need not have
+// its table rebuilt, copied into pinned memory and uploaded per launch: b2_table_create uploads
+// it once, b2_table_launch re-arms the dependency counters device-side (one D2D copy, skipped for
+// plain fan-outs) and launches.  The per-launch host cost becomes independent of the table size.
+constexpr uint32_t kMaxTables = 256;
+
+int b2_table_create(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
+                    uint32_t *table_id) {
+  if (!table_id) return fail(B2_E_ARG, "table_id is NULL");
+  if (!n || !tasks) return fail(B2_E_ARG, "empty table");
+  if (n_succ && !succ) return fail(B2_E_ARG, "succ is NULL but n_succ = %u", n_succ);
+  DEV_ORDERED(D, dev);
+  if (n > D->qcap) return fail(B2_E_NOMEM, "table of %u electrons exceeds queue capacity %u", n, D->qcap);
+  uint32_t id = 0;
+  for (; id < D->tables.size(); ++id)
+    if (!D->tables[id].live) break;
+  if (id == D->tables.size()) {
+    if (id >= kMaxTables) return fail(B2_E_NOMEM, "too many resident tables");
+    D->tables.emplace_back();
+  }
+  std::vector<b2_task> fixed(tasks, tasks + n);
+  uint32_t prefix = 0;
+  bool open = true, has_deps = false;
+  uint64_t bytes = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    b2_task &t = fixed[i];
+    bytes += (t.fn_id < B2_MAX_FN && D->h_fn_kind[t.fn_id] == B2_K_COPY) ? t.count : t.count * 4;
+    if (t.succ_count && (uint64_t)t.succ_begin + t.succ_count > n_succ)
+      return fail(B2_E_ARG, "task %u: successor range [%u, +%u) outside succ[%u]", i, t.succ_begin,
+                  t.succ_count, n_succ);
+    if (t.deps) {
+      if (t.deps >= kDepBias) return fail(B2_E_ARG, "task %u: deps too large", i);
+      t.deps += kDepBias;
+      open = false;
+      has_deps = true;
+    } else if (open) {
+      ++prefix;
+    }
+  }
+  Device::Table tb;
+  const size_t tab_bytes = (size_t)n * sizeof(b2_task);
+  CU(cudaMalloc(reinterpret_cast<void **>(&tb.d_pristine), tab_bytes + (size_t)std::max<uint32_t>(n_succ, 1) * 4));
+  if (has_deps) CU(cudaMalloc(reinterpret_cast<void **>(&tb.d_work), tab_bytes));
+  CU(cudaMalloc(reinterpret_cast<void **>(&tb.d_status), (size_t)n * 4));
+  CU(cudaMemcpyAsync(tb.d_pristine, fixed.data(), tab_bytes, cudaMemcpyHostToDevice, D->stream));
+  if (n_succ)
+    CU(cudaMemcpyAsync(tb.d_pristine + tab_bytes, succ, (size_t)n_succ * 4, cudaMemcpyHostToDevice, D->stream));
+  CU(cudaStreamSynchronize(D->stream));   // `fixed` and `succ` are pageable: they must outlive the copies
+  tb.n = n;
+  tb.n_succ = n_succ;
+  tb.prefix = prefix;
+  tb.bytes = bytes;
+  tb.has_deps = has_deps;
+  tb.live = true;
+  D->tables[id] = tb;
+  *table_id = id;
+  return B2_OK;
+}
+
+int b2_table_launch(int dev, uint32_t table_id, uint64_t status_host_off, uint64_t *ticket) {
+  Range r_("b2_table_launch");
+  DEV_ORDERED(D, dev);
+  if (table_id >= D->tables.size() || !D->tables[table_id].live)
+    return fail(B2_E_ARG, "unknown table %u", table_id);
+  Device::Table &tb = D->tables[table_id];
+  if (status_host_off != UINT64_MAX &&
+      (status_host_off + (uint64_t)tb.n * 4 > D->h_out_bytes || (status_host_off & 3)))
+    return fail(B2_E_ARG, "status_host_off %llu (+%u words) outside egress staging",
+                (unsigned long long)status_host_off, tb.n);
+  const size_t tab_bytes = (size_t)tb.n * sizeof(b2_task);
+  b2_task *d_tasks = reinterpret_cast<b2_task *>(tb.d_pristine);
+  if (tb.has_deps) {   // the worker counts the dependency words down: every launch starts from the pristine copy
+    CU(cudaMemcpyAsync(tb.d_work, tb.d_pristine, tab_bytes, cudaMemcpyDeviceToDevice, D->stream));
+    d_tasks = reinterpret_cast<b2_task *>(tb.d_work);
+  }
+  int rc = launch_worker(D, d_tasks, reinterpret_cast<const uint32_t *>(tb.d_pristine + tab_bytes), tb.d_status,
+                         tb.n, tb.prefix, tb.bytes);
+  if (rc) return rc;
+  if (status_host_off != UINT64_MAX) {
+    rc = egress_after_compute(D);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(D->h_out + status_host_off, tb.d_status, (size_t)tb.n * 4, cudaMemcpyDeviceToHost,
+                       D->egress));
+    D->egress_dirty = true;
+    D->stats.bytes_d2h += (uint64_t)tb.n * 4;
+  }
+  return record_ticket(D, ticket);
+}
+
+int b2_table_destroy(int dev, uint32_t table_id) {
+  DEV_ORDERED(D, dev);
+  if (table_id >= D->tables.size() || !D->tables[table_id].live)
+    return fail(B2_E_ARG, "unknown table %u", table_id);
+  CU(cudaStreamSynchronize(D->stream));
+  CU(cudaStreamSynchronize(D->egress));
+  Device::Table &tb = D->tables[table_id];
+  cudaFree(tb.d_pristine);
+  if (tb.d_work) cudaFree(tb.d_work);
+  cudaFree(tb.d_status);
+  tb = Device::Table();
   return B2_OK;
 }
 
@@ -1124,6 +1290,8 @@ static void submit_one(Device *D, Submission &sub) {
                           (b.flags & B2_BATCH_INDEPENDENT) != 0);
     }
     if (rc == B2_OK) {
+      if (b.flags & B2_BATCH_INDEPENDENT)   // no table scan: the operand bytes are what gets uploaded
+        D->pend_bytes = b.in_bytes ? b.in_bytes : b.n_tasks;
       D->ticket_slot[ti] = (int8_t)D->task_slot;
       D->ticket_ntasks[ti] = b.n_tasks;
       {

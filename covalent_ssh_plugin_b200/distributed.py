@@ -122,11 +122,12 @@ class _ArenaWindow:
                                          "version": 2}
 
 
-def broadcast_shared(engine, array, root: int = 0):
+def broadcast_shared(engine, array, root: int = 0, stats: dict = None):
     """A shared dependency — the same operand for electrons on every rank — is
     uploaded once on ``root`` and broadcast into every rank's arena (the only
     collective on this path).  Returns a DeviceArray that can be
-    passed as an electron argument.  ``array`` is only read on ``root``.
+    passed as an electron argument.  ``array`` is only read on ``root``.  ``stats`` (optional
+    dict) receives ``collective_seconds``, the ncclBroadcast alone.
 
     NCCL backend: ncclBroadcast directly between arenas (device to device over
     NVLink).  Other backends (gloo in the CPU tests): broadcast of the host bytes,
@@ -156,8 +157,13 @@ def broadcast_shared(engine, array, root: int = 0):
         L.call("b2_sync", engine.ordinal)
         window = _ArenaWindow(ptr.value + da.offset, nbytes)
         t = torch.as_tensor(window, device=torch.device("cuda", engine.ordinal))
+        import time
+
+        t0 = time.perf_counter()
         dist.broadcast(t, src=root)
         torch.cuda.synchronize(engine.ordinal)
+        if stats is not None:
+            stats["collective_seconds"] = time.perf_counter() - t0
         return da
     buf = torch.from_numpy(a.reshape(-1).view(np.uint8).copy()) if me == root else torch.empty(nbytes, dtype=torch.uint8)
     dist.broadcast(buf, src=root)

@@ -266,6 +266,16 @@ int b2_stage_copy(int dev, const b2_copy_job *jobs, uint32_t n);
  * running.  Best effort once the batch is on the device; exact before.  (The reference
  * cannot cancel at all: ssh.py:460-464.) */
 int b2_cancel(int dev, uint64_t ticket, uint32_t first, uint32_t count);
+/* Resident task tables: a lattice that is dispatched repeatedly (same graph, same arena offsets)
+ * uploads its table ONCE; every b2_table_launch then re-arms the dependency counters on the
+ * device and launches the worker — no table rebuild, no pinned copy, no upload per launch (the
+ * steady-state analogue of keeping function_<id>.pkl on the remote host instead of re-sending it,
+ * which the reference cannot do: ssh.py:360-361 uploads per electron).  Same record and successor
+ * conventions as b2_enqueue.  status_host_off as in b2_launch. */
+int b2_table_create(int dev, const b2_task *tasks, uint32_t n, const uint32_t *succ, uint32_t n_succ,
+                    uint32_t *table_id);
+int b2_table_launch(int dev, uint32_t table_id, uint64_t status_host_off, uint64_t *ticket);
+int b2_table_destroy(int dev, uint32_t table_id);
 /* Records a completion ticket after whatever has been queued so far. */
 int b2_mark(int dev, uint64_t *ticket);
 int b2_poll(int dev, uint64_t ticket);          /* B2_OK | B2_E_NOTREADY  (ssh.py:388-406) */

@@ -262,6 +262,33 @@ class FakeLib:
         b.ticket = t.value
         return 0
 
+    def b2_table_create(self, dev, tasks, n, succ, n_succ, idref):
+        d = self._dev(dev)
+        d.tables = getattr(d, "tables", [])
+        raw = np.frombuffer((C.c_uint8 * (64 * n)).from_address(_addr(tasks)), dtype=L.TASK_DTYPE).copy()
+        sl = list((C.c_uint32 * n_succ).from_address(_addr(succ))) if n_succ else []
+        d.tables.append((raw, sl))
+        _deref(idref).value = len(d.tables) - 1
+        return 0
+
+    def b2_table_launch(self, dev, table_id, status_off, tref):
+        d = self._dev(dev)
+        tabs = getattr(d, "tables", [])
+        if table_id >= len(tabs) or tabs[table_id] is None:
+            return self._fail(L.B2_E_ARG, "unknown table")
+        raw, sl = tabs[table_id]
+        succ = (C.c_uint32 * max(1, len(sl)))(*sl)
+        rc = self.b2_enqueue(dev, raw.ctypes.data, len(raw), succ if sl else None, len(sl), None)
+        return rc or self.b2_launch(dev, status_off, tref)
+
+    def b2_table_destroy(self, dev, table_id):
+        d = self._dev(dev)
+        tabs = getattr(d, "tables", [])
+        if table_id >= len(tabs) or tabs[table_id] is None:
+            return self._fail(L.B2_E_ARG, "unknown table")
+        tabs[table_id] = None
+        return 0
+
     def b2_cancel(self, dev, ticket, first, count):
         self.cancels = getattr(self, "cancels", []) + [(dev, ticket, first, count)]
         return 0          # the fake runs a batch inside b2_submit: nothing is left to tombstone

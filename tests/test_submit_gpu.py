@@ -183,3 +183,84 @@ def test_b2_cancel_before_the_worker_reaches_the_batch(raw_device):
     assert not cancelled[:10].any() and not cancelled[30:].any()
     assert ((st == L.TS_OK) | cancelled).all()
     assert cancelled[10:30].all(), "b2_cancel issued right after b2_submit, behind ~1 ms of work, must be exact"
+
+
+def _model_scale_add(x):
+    return np.float32(2.0) * x + np.float32(1.0)
+
+
+@pytest.mark.parametrize("elems,n", [(256, 20000), (1024, 8000), (3000, 4000), (16384, 1500), (70000, 300)])
+def test_both_worker_flavours_are_bit_exact(raw_device, elems, n):
+    """The host picks the streaming worker's flavour from the average operand size (12 x 4 KiB
+    stages and multi-ticket claims up to 8 KiB, 3 x 16 KiB stages above).  Same electrons, same
+    bytes out, whichever runs — including ragged sizes that straddle tile boundaries."""
+    L, dev = raw_device["L"], raw_device["dev"]
+    L.call("b2_register", dev, 21, L.K_SCALE_ADD, 2.0, 1.0, 0, 0)
+    rng = np.random.default_rng(elems)
+    sizes = np.maximum(1, elems + rng.integers(-elems // 8, elems // 8 + 1, n)).astype(np.int64)
+    slots = ((sizes * 4 + 255) & ~255).astype(np.int64)
+    offs = np.concatenate([[0], np.cumsum(slots)[:-1]])
+    total = int(slots.sum())
+    assert 2 * total + (64 << 20) < raw_device["arena"]
+    src = rng.standard_normal(total // 4, dtype=np.float32)
+    base_in, base_out = 128 << 20, (128 << 20) + total
+    L.call("b2_write", dev, base_in, src.ctypes.data, total)
+    L.call("b2_fill", dev, base_out, 0, total)
+    tasks = np.zeros(n, dtype=L.TASK_DTYPE)
+    tasks["fn_id"], tasks["count"] = 21, sizes
+    tasks["arg0"], tasks["out"] = base_in + offs, base_out + offs
+    L.call("b2_enqueue", dev, tasks.ctypes.data, n, None, 0, None)
+    t = C.c_uint64()
+    L.call("b2_launch", dev, 0, C.byref(t))
+    L.call("b2_wait", dev, t.value)
+    _, h_out = _host_views(L, dev)
+    assert (h_out[:4 * n].view(np.uint32) == L.TS_OK).all()
+    got = np.empty(total // 4, dtype=np.float32)
+    L.call("b2_read", dev, base_out, got.ctypes.data, total)
+    for i in list(range(0, n, max(1, n // 64))) + [n - 1]:
+        o, k = int(offs[i]) // 4, int(sizes[i])
+        assert np.array_equal(got[o:o + k], _model_scale_add(src[o:o + k])), (i, k)
+        assert not got[o + k:o + int(slots[i]) // 4].any(), "bytes beyond the electron's result were written"
+
+
+def test_resident_table_relaunches_with_dependencies(raw_device):
+    """b2_table_create uploads a table once; every b2_table_launch re-arms the dependency counters
+    on the device.  A diamond (root -> 64 fan-out -> reduce behind a gate) launched five times over
+    changing inputs gives the model's answer every time."""
+    L, dev = raw_device["L"], raw_device["dev"]
+    L.call("b2_register", dev, 21, L.K_SCALE_ADD, 2.0, 1.0, 0, 0)
+    L.call("b2_register", dev, 24, L.K_STACK_SUM, 0.0, 0.0, 0, 0)
+    fan, elems = 64, 4096
+    row = elems * 4
+    x_off, mid_off, out_off = 256 << 20, (256 << 20) + (1 << 20), (256 << 20) + (64 << 20)
+    tasks = np.zeros(fan + 2, dtype=L.TASK_DTYPE)
+    # 0: root  y = 2x+1 ; 1..fan: z_i = 2y+1 into consecutive rows ; fan+1: stack_sum of the rows
+    tasks[0]["fn_id"], tasks[0]["arg0"], tasks[0]["out"], tasks[0]["count"] = 21, x_off, x_off + row, elems
+    tasks[0]["succ_begin"], tasks[0]["succ_count"] = 0, fan
+    for i in range(1, fan + 1):
+        tasks[i]["fn_id"], tasks[i]["arg0"], tasks[i]["out"], tasks[i]["count"] = 21, x_off + row, mid_off + (i - 1) * row, elems
+        tasks[i]["deps"], tasks[i]["succ_begin"], tasks[i]["succ_count"] = 1, fan, 1
+    r = fan + 1
+    tasks[r]["fn_id"], tasks[r]["arg0"], tasks[r]["arg1"], tasks[r]["out"] = 24, mid_off, row, out_off
+    tasks[r]["count"], tasks[r]["nrows"], tasks[r]["deps"] = elems, fan, fan
+    succ = np.array(list(range(1, fan + 1)) + [r], dtype=np.uint32)
+    tid = C.c_uint32()
+    L.call("b2_table_create", dev, tasks.ctypes.data, len(tasks), succ.ctypes.data, len(succ), C.byref(tid))
+    t = C.c_uint64()
+    for rep in range(5):
+        x = np.random.default_rng(rep).random(elems, dtype=np.float32)
+        L.call("b2_write", dev, x_off, x.ctypes.data, row)
+        L.call("b2_table_launch", dev, tid.value, 0, C.byref(t))
+        L.call("b2_wait", dev, t.value)
+        _, h_out = _host_views(L, dev)
+        assert (h_out[:4 * (fan + 2)].view(np.uint32) == L.TS_OK).all(), rep
+        got = np.empty(elems, dtype=np.float32)
+        L.call("b2_read", dev, out_off, got.ctypes.data, row)
+        z = _model_scale_add(_model_scale_add(x))
+        want = z.copy()
+        for _ in range(fan - 1):
+            want = want + z                                  # row order, fp32 — as the callback adds
+        assert np.array_equal(got, want), rep
+    L.call("b2_table_destroy", dev, tid.value)
+    with pytest.raises(L.B2Error):
+        L.call("b2_table_launch", dev, tid.value, 0, C.byref(t))
