@@ -1,5 +1,14 @@
 """Warm worker processes for electrons that cannot run on a GPU (arbitrary Python).
 
+Two kinds of worker, same semantics:
+* default interpreter (``python_path`` left at "python", no ``conda_env``): a ProcessPoolExecutor
+  of this interpreter;
+* the executor names its own interpreter (``python_path`` / ``conda_env``, ssh.py:377-380 and
+  508-524 in the reference): ``hostworker.py`` started with the reference's command line
+  (``conda activate <env> && <python_path> ...``), verified the way the reference verifies the
+  remote side (conda env must exist, ``--version`` must say Python 3), kept warm, and fed
+  protocol-5 pickles whose large buffers travel through /dev/shm instead of through the pipe.
+
 OPT-IN (config key ``executors.ssh.host_pool`` or ``B2_HOST_POOL=1``): by default
 an unregistered electron takes the reference's failure decision
 (``_on_ssh_fail``) and nothing ever runs on the CPU behind the user's back.
@@ -72,10 +81,17 @@ def _get_pool() -> ProcessPoolExecutor:
     return _pool
 
 
-async def call(fn: Callable, args, kwargs, workdir: str) -> Tuple[int, str, Any, Optional[Exception]]:
+def _default_interpreter(python_path: str, conda_env: str) -> bool:
+    return not conda_env and python_path in ("", "python")
+
+
+async def call(fn: Callable, args, kwargs, workdir: str, python_path: str = "python",
+               conda_env: str = "") -> Tuple[int, str, Any, Optional[Exception]]:
     """(exit_status, stderr, result, exception) of one electron run in the pool."""
     global _pool
     stats["submitted"] += 1
+    if not _default_interpreter(python_path, conda_env or ""):
+        return await _external_call(fn, args, kwargs, workdir, python_path or "python", conda_env or "")
     try:
         blob = cloudpickle.dumps((fn, list(args), dict(kwargs)))
     except Exception as err:
@@ -110,8 +126,156 @@ def _discard(pool: ProcessPoolExecutor) -> None:
             pass
 
 
+# ---------------------------------------------------------------------------------------------
+# workers under the executor's own interpreter (python_path / conda_env)
+class _External:
+    """One warm ``hostworker.py`` process.  Plain pipes and a thread lock — not asyncio streams —
+    so that a worker outlives the event loop it was first used from (tests call asyncio.run per
+    electron; Covalent's dispatcher keeps one loop)."""
+
+    def __init__(self, proc):
+        import threading
+
+        self.proc = proc
+        self.lock = threading.Lock()
+        self.busy = 0
+        self.serial = 0
+
+    def alive(self) -> bool:
+        return self.proc.poll() is None
+
+    def roundtrip(self, frame):
+        from . import hostworker
+
+        with self.lock:
+            hostworker.send(self.proc.stdin, frame)
+            return hostworker.recv(self.proc.stdout)
+
+
+_external: dict = {}          # (python_path, conda_env) -> list of _External
+_verified: dict = {}          # (python_path, conda_env) -> "" | failure message
+
+
+def _conda_prefix(conda_env: str) -> str:
+    return f'eval "$(conda shell.bash hook)" && conda activate {conda_env} && ' if conda_env else ""
+
+
+async def _shell(cmd: str):
+    proc = await asyncio.create_subprocess_shell(cmd, stdout=asyncio.subprocess.PIPE, stderr=asyncio.subprocess.PIPE)
+    out, err = await proc.communicate()
+    return out.decode(errors="replace"), err.decode(errors="replace"), proc.returncode
+
+
+async def _verify(python_path: str, conda_env: str) -> str:
+    """The reference's two remote checks (ssh.py:508-524), once per interpreter: the conda
+    environment must be listed, and ``<python_path> --version`` must mention Python 3."""
+    key = (python_path, conda_env)
+    if key in _verified:
+        return _verified[key]
+    message = ""
+    if conda_env:
+        _, err, code = await _shell(f'eval "$(conda shell.bash hook)" && conda env list | grep {conda_env}')
+        if code != 0:
+            message = err.strip() or f"No conda environment named {conda_env} found on remote machine."
+    if not message:
+        out, err, _ = await _shell(f"{_conda_prefix(conda_env)}{python_path} --version")
+        if "3" not in (out + err).strip():          # python 2 prints its version on stderr
+            message = "No Python 3 installation found on remote machine localhost"
+    _verified[key] = message
+    return message
+
+
+def _spawn(python_path: str, conda_env: str) -> _External:
+    import subprocess
+    from pathlib import Path
+
+    from . import hostworker
+
+    worker = Path(__file__).with_name("hostworker.py")
+    cmd = f"{_conda_prefix(conda_env)}exec {python_path} {worker}"
+    proc = subprocess.Popen(cmd, shell=True, executable="/bin/bash", stdin=subprocess.PIPE, stdout=subprocess.PIPE)
+    w = _External(proc)
+    try:
+        kind, problem = hostworker.recv(proc.stdout)
+    except EOFError:
+        kind, problem = "eof", "the interpreter exited at once"
+    if kind != "hello" or problem:
+        proc.kill()
+        raise RuntimeError(f"host worker under '{python_path}' could not start: {problem or kind}")
+    return w
+
+
+async def _external_call(fn, args, kwargs, workdir: str, python_path: str, conda_env: str):
+    from . import hostworker
+
+    problem = await _verify(python_path, conda_env)
+    if problem:
+        return 1, problem, None, None
+    loop = asyncio.get_running_loop()
+    workers = _external.setdefault((python_path, conda_env), [])
+    workers[:] = [x for x in workers if x.alive()]
+    limit = int(os.environ.get("B2_HOST_POOL_WORKERS", "0")) or min(8, len(os.sched_getaffinity(0)))
+    w = next((x for x in workers if x.busy == 0), None)
+    if w is None and len(workers) < limit:
+        try:
+            w = await loop.run_in_executor(None, _spawn, python_path, conda_env)
+        except Exception as err:
+            return 1, str(err), None, None
+        workers.append(w)
+        _register_atexit()
+    if w is None:
+        w = min(workers, key=lambda x: x.busy)
+    w.busy += 1
+    shm_path = ""
+    try:
+        w.serial += 1
+        shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        try:
+            if shm_dir:
+                blob, shm_path, ranges = hostworker.pack(cloudpickle, (fn, list(args), dict(kwargs)), shm_dir,
+                                                         f"q{id(w) & 0xffff}-{w.serial}")
+            else:
+                blob, shm_path, ranges = cloudpickle.dumps((fn, list(args), dict(kwargs))), "", []
+        except Exception as err:
+            return 1, f"electron is not picklable: {err}", None, None
+        try:
+            rblob, rshm, rranges = await loop.run_in_executor(None, w.roundtrip, (blob, shm_path, ranges, workdir))
+        except (EOFError, BrokenPipeError, ConnectionResetError, OSError):
+            stats["crashed"] += 1
+            if w in workers:
+                workers.remove(w)
+            w.proc.kill()
+            if shm_path and os.path.exists(shm_path):
+                os.unlink(shm_path)
+            return 1, "worker process died while running the electron", None, None
+        (result, exception), _ = hostworker.unpack(cloudpickle, rblob, rshm, rranges)
+    finally:
+        w.busy -= 1
+    return 0, "", result, exception
+
+
+def _register_atexit() -> None:
+    global _atexit_done
+    if not _atexit_done:
+        import atexit
+
+        atexit.register(shutdown)
+        _atexit_done = True
+
+
 def shutdown() -> None:
     global _pool
     if _pool is not None:
         _discard(_pool)
         _pool = None
+    for workers in _external.values():
+        for w in workers:
+            try:
+                w.proc.kill()
+                w.proc.wait(2)
+                w.proc.stdin.close()
+                w.proc.stdout.close()
+            except Exception:
+                pass
+    _external.clear()
+    _verified.clear()

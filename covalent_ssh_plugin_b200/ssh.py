@@ -384,7 +384,8 @@ class SSHExecutor(RemoteExecutor):
         if entry is None:
             return CompletedElectron(127, f"{remote_script_file}: no such electron")
         if entry.host_call is not None:
-            code, stderr, result, exception = await hostpool.call(*entry.host_call)
+            code, stderr, result, exception = await hostpool.call(
+                *entry.host_call, python_path=self.python_path, conda_env=self.conda_env or "")
             if code == 0:
                 entry.host_result = (result, exception)
             return CompletedElectron(code, stderr)

@@ -375,3 +375,71 @@ def test_missing_key_file_raises_the_same_way_in_both_bodies(fake_lib, tmp_path)
     impl._key_is_file.clear()
     with pytest.raises(RuntimeError, match="does not exist"):
         asyncio.run(ex.run(electrons.add_int, [1, 2], {}, {"dispatch_id": "nk", "node_id": 0}))
+
+
+# ------------------------------------------------------------- host pool -------
+def _shape_and_cwd(x):
+    import os
+
+    return x * 2, os.getcwd()
+
+
+def _boom(msg):
+    raise KeyError(msg)
+
+
+def _exit_hard():
+    import os
+
+    os._exit(3)
+
+
+def test_host_pool_honours_python_path_and_conda_env(fake_lib, tmp_path):
+    """SURVEY.md §8f-2 / ssh.py:377-380, 508-524: with the pool switched on, an executor that names
+    its own interpreter gets warm workers started as `<python_path> hostworker.py` (behind
+    `conda activate <env>` when asked), verified the way the reference verifies the remote side.
+    Large arrays cross /dev/shm as protocol-5 out-of-band buffers, both ways."""
+    import os
+    import sys
+
+    import cloudpickle
+
+    import tests.test_round2_host as me
+    from covalent_ssh_plugin_b200 import hostpool
+
+    cloudpickle.register_pickle_by_value(me)
+    engine_mod.get_engine(0, **SMALL)
+    wd = tmp_path / "wd"
+    with patch.dict(os.environ, {"B2_HOST_POOL": "1", "B2_HOST_POOL_WORKERS": "2"}):
+        try:
+            ex = make_executor(tmp_path, python_path=sys.executable, remote_workdir=str(wd))
+            big = np.random.default_rng(0).standard_normal(1 << 18, dtype=np.float32)        # 1 MiB: out of band
+            async def go():
+                return await asyncio.gather(
+                    ex.run(_shape_and_cwd, [big], {}, {"dispatch_id": "pp", "node_id": 0}),
+                    ex.run(_shape_and_cwd, [np.arange(3.0)], {}, {"dispatch_id": "pp", "node_id": 1}),
+                    ex.run(_boom, ["k"], {}, {"dispatch_id": "pp", "node_id": 2}), return_exceptions=True)
+
+            (r0, cwd0), (r1, _), err = asyncio.run(go())
+            assert np.array_equal(r0, big * 2) and cwd0 == str(wd)
+            assert np.array_equal(r1, np.arange(3.0) * 2)
+            assert isinstance(err, KeyError) and err.args == ("k",)
+            assert not [p for p in os.listdir("/dev/shm") if p.startswith("b2pool-")], "shared-memory files leaked"
+            with pytest.raises(RuntimeError, match="worker process died"):
+                asyncio.run(ex.run(_exit_hard, [], {}, {"dispatch_id": "pp", "node_id": 3}))
+            # an interpreter that is not Python 3 / does not exist: the reference's message, the failure decision
+            bad = make_executor(tmp_path, python_path=str(tmp_path / "no-such-python"))
+            with pytest.raises(RuntimeError, match="No Python 3 installation found"):
+                asyncio.run(bad.run(_boom, ["x"], {}, {"dispatch_id": "pp", "node_id": 4}))
+            # a conda environment that does not exist (this image has no conda at all)
+            env = make_executor(tmp_path, python_path=sys.executable, conda_env="no_such_env")
+            with pytest.raises(RuntimeError) as ei:
+                asyncio.run(env.run(_boom, ["x"], {}, {"dispatch_id": "pp", "node_id": 5}))
+            assert "conda" in str(ei.value).lower()
+            local = make_executor(tmp_path, python_path=sys.executable, conda_env="no_such_env", run_local_on_ssh_fail=True)
+            with pytest.raises(KeyError):
+                asyncio.run(local.run(_boom, ["x"], {}, {"dispatch_id": "pp", "node_id": 6}))       # ran in process
+            # device electrons never go to the pool, whatever the interpreter settings
+            assert asyncio.run(ex.run(electrons.add_int, [2, 3], {}, {"dispatch_id": "pp", "node_id": 7})) == 5
+        finally:
+            hostpool.shutdown()
