@@ -118,6 +118,8 @@ class Stats(C.Structure):
         ("bytes_packed", C.c_uint64),
         ("bytes_h2d", C.c_uint64),
         ("bytes_d2h", C.c_uint64),
+        ("resident_instances", C.c_uint64),
+        ("resident_batches", C.c_uint64),
     ]
 
 
@@ -166,6 +168,8 @@ _SIGNATURES = {
     "b2_table_create": ([C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _u32p], True),
     "b2_table_launch": ([C.c_int, C.c_uint32, C.c_uint64, _u64p], True),
     "b2_table_destroy": ([C.c_int, C.c_uint32], True),
+    "b2_resident_enable": ([C.c_int, C.c_uint32], True),
+    "b2_resident_disable": ([C.c_int], True),
     "b2_mark": ([C.c_int, _u64p], True),
     "b2_poll": ([C.c_int, C.c_uint64], False),
     "b2_wait": ([C.c_int, C.c_uint64], True),

@@ -52,6 +52,8 @@ constexpr uint32_t kWorkerSmallSmemBytes = kSmallStages * kSmallTileBytes;
 constexpr uint32_t kHdrExit = 0xFFFFFFFFu;
 constexpr uint32_t kHdrLegacy = 0xFFFFFFFEu;
 constexpr uint32_t kHdrFailed = 0xFFFFFFFDu;          // status already decided by the producer
+constexpr uint32_t kHdrBegin = 0xFFFFFFFCu;           // a batch starts: its BatchView travels in bview[s]
+constexpr uint32_t kHdrEnd = 0xFFFFFFFBu;             // resident worker: this CTA has no more electrons of the batch
 
 struct StageHdr {
   uint8_t *out;              // global destination of this tile
@@ -75,16 +77,95 @@ __device__ __forceinline__ bool is_streaming_kind(uint32_t k) {
   return k == B2_K_COPY || k == B2_K_SCALE_ADD || k == B2_K_ADD || k == B2_K_MUL || k == B2_K_AXPY;
 }
 
-template <int kStages, uint32_t kTileBytes>
-__device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
+// What both roles need to know about the batch they are working on.  In an ordinary launch there
+// is one (built from the kernel arguments); the resident worker gets a new one per doorbell.
+struct BatchView {
+  b2_task *tasks;
+  const uint32_t *succ;
+  uint32_t *status;
+  Queue q;                 // cells / head / tail / epoch / mask of THIS batch
+  uint32_t *cursor;
+  uint32_t *finished;      // resident: CTAs that have retired their share of the batch
+  uint32_t n_tasks, prefix, claim_k, seq;
+};
+
+// ---- resident worker: control blocks -------------------------------------------------------
+// The kernel stays on the GPU across batches.  A batch is published by the host with stream-ordered
+// writes (task table, payload, ring entry, then the doorbell word) — no kernel launch — and its
+// completion is a word the egress stream waits on (cuStreamWaitValue32) before it downloads.
+constexpr uint32_t kResRing = 64;            // batches that may be published ahead of the worker
+constexpr uint32_t kResNone = 0xFFFFFFFFu;
+
+struct ResidentBatch {     // one ring entry (device memory, written by the host through the upload stream)
+  b2_task *tasks;
+  const uint32_t *succ;
+  uint32_t *status;
+  uint32_t n_tasks, prefix, claim_k, pad;
+  uint64_t pad2[3];
+};
+struct ResidentQ {         // per-batch queue counters (zero when the slot is handed to a batch)
+  uint32_t head, tail, cursor, finished;
+  uint32_t pad[12];
+};
+struct ResidentCtl {       // device memory
+  ResidentBatch ring[kResRing];
+  ResidentQ q[kResRing];
+  uint32_t doorbell;       // batches published so far        (host: stream memory op on the upload stream)
+  uint32_t pad0[31];
+  uint32_t approved;       // batches every CTA may start     (leader CTA)
+  uint32_t exit_at;        // leave when reaching this batch  (leader CTA; kResNone = stay)
+  uint32_t pad1[30];
+  uint32_t done;           // batches completed               (last CTA of each batch; the egress stream waits on it)
+  uint32_t pad2[31];
+};
+struct ResidentHost {      // mapped pinned host memory: the two words of the exit handshake
+  volatile uint32_t submitted;   // host -> kernel: batches the host has submitted (written BEFORE their stream ops)
+  volatile uint32_t stop;        // host -> kernel: leave as soon as nothing submitted is pending
+  volatile uint32_t state;       // kernel -> host: (instance << 2) | 1 running | 2 leaving
+  volatile uint32_t error;       // kernel -> host: 1 = a submitted batch never arrived (lifetime cap hit)
+};
+struct ResidentArgs {
+  ResidentCtl *ctl;
+  ResidentHost *host;      // device pointer of the mapped block
+  uint32_t instance;
+  uint32_t idle_us;        // leave after this long without a published batch ...
+  uint32_t life_ms;        // ... and never stay longer than this (bounded even if the host misbehaves)
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int kStages, uint32_t kTileBytes, bool kResident>
+__device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const ResidentArgs &ra) {
   extern __shared__ __align__(128) uint8_t stage_mem[];   // kStages x kTileBytes, dynamic
   __shared__ StageHdr hdr[kStages];
   __shared__ Slot legacy[kStages];
+  __shared__ BatchView bview[kStages];                    // travels with kHdrBegin
+  __shared__ BatchView wv;                                // the batch the worker warps are on
   __shared__ __align__(8) unsigned long long full_bar[kStages];
   __shared__ __align__(8) unsigned long long empty_bar[kStages];
   __shared__ uint32_t s_base;
   __shared__ uint32_t s_status;
-  const uint32_t P = a.n_ready_prefix;
   constexpr int kWorkerWarps = kWorkerThreads / kWarp;
 
   if (threadIdx.x == 0) {
@@ -108,165 +189,263 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
         if (use >= 1) mbar_wait(smem_addr(&empty_bar[s]), (use - 1) & 1u);
         return s;
       };
-      // The producer always holds one claimed ticket beyond the electron it is streaming,
-      // and — when that ticket lies in the ready prefix — its task record is already on its
-      // way into registers: the fetch-add and the record's L2 round trips overlap the tile
-      // issue of the current electron instead of sitting between two electrons.
-      // Tickets are claimed a.claim_k at a time (one fetch-add on the shared head per K electrons:
-      // with electrons of a few KiB the single-address atomic is otherwise the rate limiter).  A CTA
-      // runs its tickets in increasing order, so a ticket that has to wait for its cell never sits
-      // in front of a published one: cells are published in ticket order.
-      const uint32_t K = a.claim_k ? a.claim_k : 1u;
-      uint32_t claimed_end = 0;            // one past the last ticket of the current claim
-      auto next_ticket = [&](uint32_t after) -> uint32_t {
-        if (after + 1 < claimed_end) return after + 1;
-        const uint32_t base = queue_claim_n(a.q, K);
-        claimed_end = base + K;
-        return base;
+      auto marker = [&](uint32_t kind, const BatchView *v) {
+        const uint32_t s = acquire();
+        hdr[s].kind = kind;
+        if (v) bview[s] = *v;
+        mbar_arrive(smem_addr(&full_bar[s]));
+        ++it;
       };
-      uint32_t ticket = queue_claim_n(a.q, K);
-      claimed_end = ticket + K;
-      b2_task t_next = {};
-      if (ticket < P) t_next = a.tasks[ticket];
-      for (;;) {
-        const uint32_t cur = ticket;
-        uint32_t ti;
-        b2_task t;
-        if (cur < P) {
-          ti = cur;
-          t = t_next;
-        } else {
-          ti = queue_take(a.q, cur, a.n_tasks);
-          // a released dependent reads what other SMs just wrote with ordinary stores: order
-          // the acquire above before the copy engine's (async proxy) reads below
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          if (ti != kNoTask) t = a.tasks[ti];
-        }
-        if (ti == kNoTask) {
-          const uint32_t s = acquire();
-          hdr[s].kind = kHdrExit;
-          mbar_arrive(smem_addr(&full_bar[s]));
-          break;
-        }
-        ticket = next_ticket(cur);
-        if (ticket < P) t_next = a.tasks[ticket];
-        uint32_t kind = B2_K__COUNT;
-        FnEntry fn;
-        fn.kind = 0; fn.alpha = 0.f; fn.beta = 0.f; fn.pad = 0; fn.ialpha = 0; fn.ibeta = 0;
-        if (t.fn_id < B2_MAX_FN) {
-          fn = a.fn_table[t.fn_id];
-          kind = fn.kind;
-          if (kind >= B2_K__COUNT || (kind == B2_K_NONE && t.fn_id != 0)) kind = B2_K__COUNT;
-        }
-        if (t.flags & B2_F_CANCELLED) {
-          // tombstone (b2_cancel): nothing runs, the status says so, successors are still released
-          const uint32_t s = acquire();
-          StageHdr &h = hdr[s];
-          h.kind = kHdrFailed;
-          h.status = B2_TS_CANCELLED;
-          h.task = ti;
-          h.last = 1;
-          h.succ_begin = t.succ_begin;
-          h.succ_count = t.succ_count;
-          mbar_arrive(smem_addr(&full_bar[s]));
-          ++it;
-          continue;
-        }
-        if (kind == B2_K__COUNT || !is_streaming_kind(kind)) {
-          // one stage carries the whole electron: bad fn_id, or a callback that reads global
-          // memory itself (SUM, STACK_SUM, integer electrons, the gate)
-          const uint32_t s = acquire();
-          StageHdr &h = hdr[s];
-          h.task = ti;
-          h.last = 1;
-          h.succ_begin = t.succ_begin;
-          h.succ_count = t.succ_count;
-          if (kind == B2_K__COUNT) {
+
+      // Streams every electron this CTA claims from batch v (tickets in increasing order).
+      auto produce = [&](const BatchView &v) {
+        const uint32_t P = v.prefix;
+        // The producer always holds one claimed ticket beyond the electron it is streaming,
+        // and — when that ticket lies in the ready prefix — its task record is already on its
+        // way into registers: the fetch-add and the record's L2 round trips overlap the tile
+        // issue of the current electron instead of sitting between two electrons.
+        // Tickets are claimed claim_k at a time (one fetch-add on the shared head per K electrons:
+        // with electrons of a few KiB the single-address atomic is otherwise the rate limiter).  A CTA
+        // runs its tickets in increasing order, so a ticket that has to wait for its cell never sits
+        // in front of a published one: cells are published in ticket order.
+        const uint32_t K = v.claim_k ? v.claim_k : 1u;
+        uint32_t claimed_end = 0;            // one past the last ticket of the current claim
+        auto next_ticket = [&](uint32_t after) -> uint32_t {
+          if (after + 1 < claimed_end) return after + 1;
+          const uint32_t base = queue_claim_n(v.q, K);
+          claimed_end = base + K;
+          return base;
+        };
+        uint32_t ticket = queue_claim_n(v.q, K);
+        claimed_end = ticket + K;
+        b2_task t_next = {};
+        if (ticket < P) t_next = v.tasks[ticket];
+        for (;;) {
+          const uint32_t cur = ticket;
+          uint32_t ti;
+          b2_task t;
+          if (cur < P) {
+            ti = cur;
+            t = t_next;
+          } else {
+            ti = queue_take(v.q, cur, v.n_tasks);
+            // a released dependent reads what other SMs just wrote with ordinary stores: order
+            // the acquire above before the copy engine's (async proxy) reads below
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            if (ti != kNoTask) t = v.tasks[ti];
+          }
+          if (ti == kNoTask) return;
+          ticket = next_ticket(cur);
+          if (ticket < P) t_next = v.tasks[ticket];
+          uint32_t kind = B2_K__COUNT;
+          FnEntry fn;
+          fn.kind = 0; fn.alpha = 0.f; fn.beta = 0.f; fn.pad = 0; fn.ialpha = 0; fn.ibeta = 0;
+          if (t.fn_id < B2_MAX_FN) {
+            fn = a.fn_table[t.fn_id];
+            kind = fn.kind;
+            if (kind >= B2_K__COUNT || (kind == B2_K_NONE && t.fn_id != 0)) kind = B2_K__COUNT;
+          }
+          if (t.flags & B2_F_CANCELLED) {
+            // tombstone (b2_cancel): nothing runs, the status says so, successors are still released
+            const uint32_t s = acquire();
+            StageHdr &h = hdr[s];
             h.kind = kHdrFailed;
-            h.status = B2_TS_BAD_FN;
-          } else {
-            h.kind = kHdrLegacy;
-            legacy[s].t = t;
-            legacy[s].fn = fn;
-            legacy[s].index = ti;
-            legacy[s].kind = kind;
+            h.status = B2_TS_CANCELLED;
+            h.task = ti;
+            h.last = 1;
+            h.succ_begin = t.succ_begin;
+            h.succ_count = t.succ_count;
+            mbar_arrive(smem_addr(&full_bar[s]));
+            ++it;
+            continue;
           }
-          mbar_arrive(smem_addr(&full_bar[s]));
-          ++it;
-          continue;
-        }
-        // ---- streaming electron: resolve once, then tile after tile -----------------
-        const bool two = (kind == B2_K_ADD || kind == B2_K_MUL || kind == B2_K_AXPY);
-        const uint64_t bytes = (kind == B2_K_COPY) ? t.count : t.count * 4;
-        bool ok = true;
-        const uint8_t *p0 = resolve(a, (t.flags >> B2_F_ARENA0_SHIFT) & 15u, t.arg0, bytes, &ok);
-        const uint8_t *p1 = two ? resolve(a, (t.flags >> B2_F_ARENA1_SHIFT) & 15u, t.arg1, bytes, &ok)
-                                : nullptr;
-        uint8_t *po = resolve(a, (t.flags >> B2_F_ARENAO_SHIFT) & 15u, t.out, bytes, &ok);
-        if ((t.flags & (B2_F_IMM0 | (two ? B2_F_IMM1 : 0u))) || !ok || !aligned16(p0) ||
-            !aligned16(po) || (two && !aligned16(p1))) {
-          const uint32_t s = acquire();
-          StageHdr &h = hdr[s];
-          h.kind = kHdrFailed;
-          h.status = B2_TS_BAD_ARG;
-          h.task = ti;
-          h.last = 1;
-          h.succ_begin = t.succ_begin;
-          h.succ_count = t.succ_count;
-          mbar_arrive(smem_addr(&full_bar[s]));
-          ++it;
-          continue;
-        }
-        const uint32_t per_tile = two ? kTileBytes / 2 : kTileBytes;
-        uint64_t off = 0;
-        do {
-          const uint64_t left = bytes - off;
-          const uint32_t chunk = left < per_tile ? (uint32_t)left : per_tile;
-          const bool last = (off + chunk == bytes);
-          const uint32_t b16 = chunk & ~15u;
-          const uint32_t s = acquire();
-          StageHdr &h = hdr[s];
-          h.out = po + off;
-          h.tail0 = p0 + off + b16;
-          h.tail1 = two ? p1 + off + b16 : nullptr;
-          h.n_vec = b16 >> 4;
-          h.tail_bytes = chunk - b16;
-          h.kind = kind;
-          h.last = last ? 1u : 0u;
-          h.task = ti;
-          h.alpha = fn.alpha;
-          h.beta = fn.beta;
-          h.succ_begin = t.succ_begin;
-          h.succ_count = t.succ_count;
-          const uint32_t fb = smem_addr(&full_bar[s]);
-          if (b16) {
-            const uint32_t dst = smem_addr(stage_mem) + s * kTileBytes;
-            mbar_expect_tx(fb, two ? 2 * b16 : b16);
-            bulk_g2s(dst, p0 + off, b16, fb);
-            if (two) bulk_g2s(dst + kTileBytes / 2, p1 + off, b16, fb);
-          } else {
-            mbar_arrive(fb);
+          if (kind == B2_K__COUNT || !is_streaming_kind(kind)) {
+            // one stage carries the whole electron: bad fn_id, or a callback that reads global
+            // memory itself (SUM, STACK_SUM, integer electrons, the gate)
+            const uint32_t s = acquire();
+            StageHdr &h = hdr[s];
+            h.task = ti;
+            h.last = 1;
+            h.succ_begin = t.succ_begin;
+            h.succ_count = t.succ_count;
+            if (kind == B2_K__COUNT) {
+              h.kind = kHdrFailed;
+              h.status = B2_TS_BAD_FN;
+            } else {
+              h.kind = kHdrLegacy;
+              legacy[s].t = t;
+              legacy[s].fn = fn;
+              legacy[s].index = ti;
+              legacy[s].kind = kind;
+            }
+            mbar_arrive(smem_addr(&full_bar[s]));
+            ++it;
+            continue;
           }
-          ++it;
-          off += chunk;
-        } while (off < bytes);
+          // ---- streaming electron: resolve once, then tile after tile -----------------
+          const bool two = (kind == B2_K_ADD || kind == B2_K_MUL || kind == B2_K_AXPY);
+          const uint64_t bytes = (kind == B2_K_COPY) ? t.count : t.count * 4;
+          bool ok = true;
+          const uint8_t *p0 = resolve(a, (t.flags >> B2_F_ARENA0_SHIFT) & 15u, t.arg0, bytes, &ok);
+          const uint8_t *p1 = two ? resolve(a, (t.flags >> B2_F_ARENA1_SHIFT) & 15u, t.arg1, bytes, &ok)
+                                  : nullptr;
+          uint8_t *po = resolve(a, (t.flags >> B2_F_ARENAO_SHIFT) & 15u, t.out, bytes, &ok);
+          if ((t.flags & (B2_F_IMM0 | (two ? B2_F_IMM1 : 0u))) || !ok || !aligned16(p0) ||
+              !aligned16(po) || (two && !aligned16(p1))) {
+            const uint32_t s = acquire();
+            StageHdr &h = hdr[s];
+            h.kind = kHdrFailed;
+            h.status = B2_TS_BAD_ARG;
+            h.task = ti;
+            h.last = 1;
+            h.succ_begin = t.succ_begin;
+            h.succ_count = t.succ_count;
+            mbar_arrive(smem_addr(&full_bar[s]));
+            ++it;
+            continue;
+          }
+          const uint32_t per_tile = two ? kTileBytes / 2 : kTileBytes;
+          uint64_t off = 0;
+          do {
+            const uint64_t left = bytes - off;
+            const uint32_t chunk = left < per_tile ? (uint32_t)left : per_tile;
+            const bool last = (off + chunk == bytes);
+            const uint32_t b16 = chunk & ~15u;
+            const uint32_t s = acquire();
+            StageHdr &h = hdr[s];
+            h.out = po + off;
+            h.tail0 = p0 + off + b16;
+            h.tail1 = two ? p1 + off + b16 : nullptr;
+            h.n_vec = b16 >> 4;
+            h.tail_bytes = chunk - b16;
+            h.kind = kind;
+            h.last = last ? 1u : 0u;
+            h.task = ti;
+            h.alpha = fn.alpha;
+            h.beta = fn.beta;
+            h.succ_begin = t.succ_begin;
+            h.succ_count = t.succ_count;
+            const uint32_t fb = smem_addr(&full_bar[s]);
+            if (b16) {
+              const uint32_t dst = smem_addr(stage_mem) + s * kTileBytes;
+              mbar_expect_tx(fb, two ? 2 * b16 : b16);
+              bulk_g2s(dst, p0 + off, b16, fb);
+              if (two) bulk_g2s(dst + kTileBytes / 2, p1 + off, b16, fb);
+            } else {
+              mbar_arrive(fb);
+            }
+            ++it;
+            off += chunk;
+          } while (off < bytes);
+        }
+      };
+
+      if (!kResident) {
+        BatchView v;
+        v.tasks = a.tasks;
+        v.succ = a.succ;
+        v.status = a.status;
+        v.q = a.q;
+        v.cursor = a.cursor;
+        v.finished = nullptr;
+        v.n_tasks = a.n_tasks;
+        v.prefix = a.n_ready_prefix;
+        v.claim_k = a.claim_k;
+        v.seq = 0;
+        marker(kHdrBegin, &v);
+        produce(v);
+        marker(kHdrExit, nullptr);
+      } else {
+        // ------------------------------------------------------- resident: batch after batch --
+        ResidentCtl *ctl = ra.ctl;
+        const unsigned long long born = global_ns();
+        const unsigned long long idle_ns = (unsigned long long)ra.idle_us * 1000ull;
+        const unsigned long long life_ns = (unsigned long long)ra.life_ms * 1000000ull;
+        // Every CTA of an instance starts at the same batch: none can complete before all CTAs
+        // of the instance have passed through it.
+        uint32_t b = ld_acquire_gpu_u32(&ctl->done);
+        for (;;) {
+          if (blockIdx.x == 0) {
+            // The leader decides, for every CTA alike, whether batch b runs or the instance leaves.
+            unsigned long long t0 = global_ns();
+            uint32_t spins = 0;
+            ra.host->state = (ra.instance << 2) | 1u;
+            for (;;) {
+              const uint32_t published = ld_acquire_sys_u32(&ctl->doorbell);
+              if ((int32_t)(published - b) > 0) {
+                // at most two batches are in flight (two sets of queue cells): b starts once b-2 is done
+                const uint32_t dn = ld_acquire_gpu_u32(&ctl->done);
+                if ((int32_t)(b - dn) <= 1) {
+                  st_release_gpu_u32(&ctl->approved, b + 1);
+                  break;
+                }
+                __nanosleep(128);
+              } else {
+                const unsigned long long now = global_ns();
+                const bool expired = now - born > life_ns;
+                const bool asked = ((++spins & 15u) == 0u) && ra.host->stop != 0u;   // b2_resident_disable / quiesce
+                if (now - t0 > idle_ns || expired || asked) {
+                  // exit handshake with the host (Dekker): announce, fence, then look at what the host
+                  // has submitted.  The host writes `submitted` before it issues a batch's stream
+                  // operations and reads `state` afterwards — one of the two sees the other.
+                  ra.host->state = (ra.instance << 2) | 2u;
+                  __threadfence_system();
+                  const uint32_t sub = ra.host->submitted;
+                  if ((int32_t)(sub - b) > 0 && !expired) {
+                    ra.host->state = (ra.instance << 2) | 1u;     // a batch is on its way: stay
+                    t0 = now;
+                  } else {
+                    if ((int32_t)(sub - b) > 0) ra.host->error = 1u;   // lifetime cap with work pending
+                    __threadfence_system();
+                    st_release_gpu_u32(&ctl->exit_at, b);
+                    break;
+                  }
+                }
+                __nanosleep(256);
+              }
+            }
+          }
+          bool leave = false;
+          for (uint32_t backoff = 32;;) {
+            if ((int32_t)(ld_acquire_gpu_u32(&ctl->approved) - b) > 0) break;
+            if (ld_acquire_gpu_u32(&ctl->exit_at) == b) {
+              leave = true;
+              break;
+            }
+            __nanosleep(backoff);
+            if (backoff < 512) backoff <<= 1;
+          }
+          if (leave) break;
+          // the ring entry, the table and the payload were written by the copy engine before the
+          // doorbell: the acquire chain (doorbell -> approved) orders them before these reads
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          const volatile ResidentBatch *rb = &ctl->ring[b % kResRing];
+          ResidentQ *rq = &ctl->q[b % kResRing];
+          BatchView v;
+          v.tasks = rb->tasks;
+          v.succ = rb->succ;
+          v.status = rb->status;
+          v.q.cells = a.q.cells + (size_t)(b & 1u) * ((size_t)a.q.mask + 1);
+          v.q.head = &rq->head;
+          v.q.tail = &rq->tail;
+          v.q.epoch = b + 1u;
+          v.q.mask = a.q.mask;
+          v.cursor = &rq->cursor;
+          v.finished = &rq->finished;
+          v.n_tasks = rb->n_tasks;
+          v.prefix = rb->prefix;
+          v.claim_k = rb->claim_k;
+          v.seq = b;
+          marker(kHdrBegin, &v);
+          produce(v);
+          marker(kHdrEnd, nullptr);
+          ++b;
+        }
+        marker(kHdrExit, nullptr);
       }
     }
   } else {
     // --------------------------------------------------------------- worker warps --
-    if (P < a.n_tasks) {   // publish ready electrons that sit behind a dependent one in the table
-      for (;;) {
-        if (threadIdx.x == 0) s_base = P + atomicAdd(a.cursor, (uint32_t)kWorkerThreads);
-        worker_sync();
-        const uint32_t base = s_base;
-        worker_sync();
-        if (base >= a.n_tasks) break;
-        const uint32_t i = base + threadIdx.x;
-        const bool ready = (i < a.n_tasks) && (a.tasks[i].deps == 0);
-        queue_push_warp(a.q, P, ready, i);
-      }
-    }
-
     const int lane = threadIdx.x & 31;
     for (uint32_t it = 0;; ++it) {
       const uint32_t s = it % kStages;
@@ -274,6 +453,46 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
       const StageHdr &h = hdr[s];
       const uint32_t kind = h.kind;
       if (kind == kHdrExit) break;
+      if (kind == kHdrBegin) {
+        worker_sync();                                  // nobody still reads the previous batch's view
+        if (threadIdx.x == 0) wv = bview[s];
+        worker_sync();
+        const uint32_t P = wv.prefix;
+        if (P < wv.n_tasks) {   // publish ready electrons that sit behind a dependent one in the table
+          for (;;) {
+            if (threadIdx.x == 0) s_base = P + atomicAdd(wv.cursor, (uint32_t)kWorkerThreads);
+            worker_sync();
+            const uint32_t base = s_base;
+            worker_sync();
+            if (base >= wv.n_tasks) break;
+            const uint32_t i = base + threadIdx.x;
+            const bool ready = (i < wv.n_tasks) && (wv.tasks[i].deps == 0);
+            queue_push_warp(wv.q, P, ready, i);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
+        continue;
+      }
+      if (kind == kHdrEnd) {
+        // resident: this CTA has retired its share of the batch.  The last CTA to say so completes
+        // the batch: re-arms the slot's counters and publishes `done` for the egress stream.
+        worker_sync();                                  // every store of this CTA for the batch is issued
+        if (threadIdx.x == 0) {
+          __threadfence_system();                       // ... and visible to the copy engine
+          if (atomicAdd(wv.finished, 1u) == gridDim.x - 1) {
+            *wv.q.head = 0;
+            *wv.q.tail = 0;
+            *wv.cursor = 0;
+            *wv.finished = 0;
+            __threadfence_system();
+            st_release_sys_u32(&ra.ctl->done, wv.seq + 1u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
+        continue;
+      }
       uint32_t status = B2_TS_OK;
       if (kind == kHdrFailed) {
         status = h.status;
@@ -359,19 +578,19 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
         const uint32_t ti = h.task, succ_begin = h.succ_begin, succ_count = h.succ_count;
         if (threadIdx.x == 0) s_status = status;
         worker_sync();  // every result store of this electron is ordered before what follows
-        if (threadIdx.x == 0) a.status[ti] = s_status;
+        if (threadIdx.x == 0) wv.status[ti] = s_status;
         for (uint32_t base = 0; base < succ_count; base += kWorkerThreads) {
           const uint32_t e = base + threadIdx.x;
           bool fire = false;
           uint32_t sidx = 0;
           if (e < succ_count) {
-            sidx = a.succ[succ_begin + e];
-            if (sidx < a.n_tasks) {
+            sidx = wv.succ[succ_begin + e];
+            if (sidx < wv.n_tasks) {
               __threadfence();
-              fire = (atomicSub(&a.tasks[sidx].deps, 1u) == kDepBias + 1u);
+              fire = (atomicSub(&wv.tasks[sidx].deps, 1u) == kDepBias + 1u);
             }
           }
-          queue_push_warp(a.q, P, fire, sidx);
+          queue_push_warp(wv.q, wv.prefix, fire, sidx);
         }
       }
       // hand the stage back: one arrival per worker warp, after the whole warp has read it
@@ -381,7 +600,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
   }
 
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (!kResident && threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(a.exited, 1u) == gridDim.x - 1) {
       *a.q.head = 0;
@@ -395,12 +614,20 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a) {
 
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
-  worker_tma_body<kStages, kTileBytes>(a);
+  worker_tma_body<kStages, kTileBytes, false>(a, ResidentArgs{});
 }
 
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_small_kernel(const __grid_constant__ WorkerArgs a) {
-  worker_tma_body<kSmallStages, kSmallTileBytes>(a);
+  worker_tma_body<kSmallStages, kSmallTileBytes, false>(a, ResidentArgs{});
+}
+
+// The resident worker: one CTA set that outlives its batches (b2_resident_enable).  `a` supplies
+// what does not change between batches (callback table, arenas, the two sets of queue cells);
+// everything per batch comes through the ring in `ra.ctl`.
+__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
+    worker_resident_kernel(const __grid_constant__ WorkerArgs a, const __grid_constant__ ResidentArgs ra) {
+  worker_tma_body<kStages, kTileBytes, true>(a, ra);
 }
 
 }  // namespace b2

@@ -12,11 +12,13 @@
 // callback table.  Host-side tables that a kernel reads are staged through
 // small event-guarded pinned rings so that calls never block on the GPU unless
 // the ring wraps.
+#include <cuda.h>   // types and flags of the stream memory operations (entry points are looked up at run time)
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -133,6 +135,21 @@ struct Device {
   int worker_small_ctas_per_sm = 0;
   int worker_small_mode = -1;    // B2_WORKER_SMALL: -1 auto (by average operand size), 0 never, 1 always
   int claim_k_override = 0;      // B2_CLAIM_K
+  // resident worker (b2_resident_enable): one kernel instance outlives its batches
+  bool res_enabled = false;
+  bool res_live = false;           // an instance has been launched and may still be running
+  cudaStream_t res_stream = nullptr;
+  ResidentCtl *d_ctl = nullptr;
+  ResidentHost *h_res = nullptr, *d_res = nullptr;   // mapped pinned block: host / device address
+  ResidentBatch *h_ring = nullptr;                   // pinned source of the ring entries
+  uint32_t *h_const = nullptr;                       // pinned constants for stream-ordered word writes
+  cudaEvent_t ring_ev[kResRing] = {};
+  uint32_t res_submitted = 0;      // sequence number of the next batch
+  uint32_t res_instance = 0;
+  uint32_t res_idle_us = 200, res_life_ms = 2000;
+  int res_ctas_per_sm = 0;         // every CTA of an instance must be co-resident (they wait for each other)
+  uint64_t res_batches = 0, res_launches = 0;
+  bool compute_dirty = false;      // real work sits on the compute stream that a later batch may depend on
   struct Table {                 // resident task table (b2_table_create)
     uint8_t *d_pristine = nullptr;   // [n tasks][n_succ successor indices] as uploaded
     uint8_t *d_work = nullptr;       // working copy of the tasks (dependency counters are consumed)
@@ -174,6 +191,8 @@ struct Device {
 };
 
 Device g_dev[kMaxDevices];
+
+int resident_quiesce(Device *D);
 
 Device *get(int dev) {
   if (dev < 0 || dev >= kMaxDevices) return nullptr;
@@ -243,6 +262,10 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
                       uint32_t dst_id) {
   if (n == 0) return B2_OK;
   if (!spans) return fail(B2_E_ARG, "spans is NULL");
+  {   // another kernel needs the SMs: ask a resident instance to leave now rather than at its idle timeout
+    int rc_ = resident_quiesce(D);
+    if (rc_) return rc_;
+  }
   if (src_id >= (uint32_t)D->n_arenas || dst_id >= (uint32_t)D->n_arenas)
     return fail(B2_E_ARG, "arena id out of range (src %u, dst %u, have %d)", src_id, dst_id,
                 D->n_arenas);
@@ -323,6 +346,7 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
   CU(cudaGetLastError());
   CU(cudaEventRecord(s.ev, D->stream));
   s.in_flight = true;
+  D->compute_dirty = true;
   D->stats.launches_pack += 1;
   D->stats.bytes_packed += moved;
   return B2_OK;
@@ -348,12 +372,140 @@ int env_int(const char *name, int dflt) {
   return atoi(v);
 }
 
+// ------------------------------------------------------------ resident worker --
+// Stream memory operations (driver API) looked up through the runtime, so that the library does
+// not link against libcuda: the doorbell is a 32-bit word the upload stream WRITES after the batch's
+// table / payload / ring entry, completion is a word the compute stream WAITS on.
+typedef CUresult (*stream_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+stream_value32_fn g_write32 = nullptr, g_wait32 = nullptr;
+
+int load_stream_memops() {
+  if (g_write32 && g_wait32) return B2_OK;
+  cudaDriverEntryPointQueryResult q1, q2;
+  void *w = nullptr, *v = nullptr;
+  CU(cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q1));
+  CU(cudaGetDriverEntryPoint("cuStreamWaitValue32", &v, cudaEnableDefault, &q2));
+  if (!w || !v || q1 != cudaDriverEntryPointSuccess || q2 != cudaDriverEntryPointSuccess)
+    return fail(B2_E_UNSUPPORTED, "stream memory operations are not available in this driver");
+  g_write32 = reinterpret_cast<stream_value32_fn>(w);
+  g_wait32 = reinterpret_cast<stream_value32_fn>(v);
+  return B2_OK;
+}
+
+#define CUD(call)                                                                      \
+  do {                                                                                 \
+    CUresult r_ = (call);                                                              \
+    if (r_ != CUDA_SUCCESS)                                                            \
+      return fail(B2_E_CUDA, "%s -> CUresult %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+  } while (0)
+
+void fill_worker_consts(Device *D, WorkerArgs &a) {
+  memset(&a, 0, sizeof a);
+  a.fn_table = D->d_fn;
+  a.q.cells = D->d_cells;
+  a.q.head = D->d_head;
+  a.q.tail = D->d_tail;
+  a.q.mask = D->qcap - 1;
+  a.cursor = D->d_cursor;
+  a.exited = D->d_exited;
+  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
+    a.arena[i] = D->arena[i];
+    a.arena_bytes[i] = D->arena_bytes[i];
+  }
+}
+
+// Launches one instance of the resident kernel (it leaves by itself when idle; see the exit
+// handshake in b2_worker_tma.cuh).  Stream-ordered after the previous instance.
+int resident_launch_instance(Device *D) {
+  D->res_instance += 1;
+  D->h_const[0] = kResNone;
+  CU(cudaMemcpyAsync(&D->d_ctl->exit_at, &D->h_const[0], 4, cudaMemcpyHostToDevice, D->res_stream));
+  WorkerArgs a;
+  fill_worker_consts(D, a);
+  a.q.cells = D->d_cells + D->qcap;          // the resident worker's two cell sets
+  ResidentArgs ra;
+  memset(&ra, 0, sizeof ra);
+  ra.ctl = D->d_ctl;
+  ra.host = D->d_res;
+  ra.instance = D->res_instance;
+  ra.idle_us = D->res_idle_us;
+  ra.life_ms = D->res_life_ms;
+  const int grid = D->sm_count * std::max(1, D->res_ctas_per_sm);   // all of them resident at once, by construction
+  worker_resident_kernel<<<grid, kCtaThreads, kWorkerSmemBytes, D->res_stream>>>(a, ra);
+  CU(cudaGetLastError());
+  D->res_live = true;
+  D->res_launches += 1;
+  D->stats.launches_worker += 1;
+  return B2_OK;
+}
+
+// Publishes one batch to the resident worker instead of launching a kernel for it.
+int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32_t *d_status, uint32_t n,
+                     uint32_t prefix, uint64_t operand_bytes) {
+  const uint32_t seq = D->res_submitted;
+  const uint32_t slot = seq % kResRing;
+  if (D->ring_ev[slot]) CU(cudaEventSynchronize(D->ring_ev[slot]));   // the slot's previous upload has left pinned memory
+  else CU(cudaEventCreateWithFlags(&D->ring_ev[slot], cudaEventDisableTiming));
+  const uint64_t avg = n ? operand_bytes / n : 0;
+  const int grid = D->sm_count * std::max(1, D->res_ctas_per_sm);
+  uint32_t k = 1;
+  if (operand_bytes) k = avg <= 2048 ? 8u : avg <= 8192 ? 4u : avg <= 32768 ? 2u : 1u;
+  while (k > 1 && (uint64_t)grid * k * 4 > n) k >>= 1;
+  if (D->claim_k_override > 0) k = (uint32_t)D->claim_k_override;
+  ResidentBatch &rb = D->h_ring[slot];
+  memset(&rb, 0, sizeof rb);
+  rb.tasks = d_tasks;
+  rb.succ = d_succ;
+  rb.status = d_status;
+  rb.n_tasks = n;
+  rb.prefix = prefix;
+  rb.claim_k = k;
+  // exit handshake, host half: announce the batch BEFORE any of its stream operations, then look
+  // at the kernel's state.  If the instance we launched last is leaving, queue another one behind it.
+  D->h_res->submitted = seq + 1;
+  __sync_synchronize();
+  const uint32_t st = D->h_res->state;
+  if (!D->res_live || ((st & 3u) == 2u && (st >> 2) == D->res_instance)) {
+    int rc = resident_launch_instance(D);
+    if (rc) return rc;
+  }
+  if (D->compute_dirty) {   // e.g. a b2_h2d this batch reads from: the doorbell must not overtake it
+    CU(cudaEventRecord(D->to_egress, D->stream));
+    CU(cudaStreamWaitEvent(D->upload, D->to_egress, 0));
+    D->compute_dirty = false;
+  }
+  if (seq >= kResRing)      // the ring entry being replaced belongs to a batch that must have completed
+    CUD(g_wait32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->done, seq - kResRing + 1, CU_STREAM_WAIT_VALUE_GEQ));
+  CU(cudaMemcpyAsync(&D->d_ctl->ring[slot], &rb, sizeof rb, cudaMemcpyHostToDevice, D->upload));
+  CU(cudaEventRecord(D->ring_ev[slot], D->upload));
+  CUD(g_write32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->doorbell, seq + 1, CU_STREAM_WRITE_VALUE_DEFAULT));
+  // everything queued on the compute stream after this point is ordered after the batch: the
+  // existing egress / ticket logic (events recorded on the compute stream) needs no other change
+  CUD(g_wait32(D->stream, (CUdeviceptr)(uintptr_t)&D->d_ctl->done, seq + 1, CU_STREAM_WAIT_VALUE_GEQ));
+  D->res_submitted = seq + 1;
+  D->res_batches += 1;
+  D->stats.electrons += n;
+  return B2_OK;
+}
+
+// Makes the resident instance leave now (it finishes what has been submitted first).
+int resident_quiesce(Device *D) {
+  if (!D->res_live) return B2_OK;
+  D->h_res->stop = 1;
+  __sync_synchronize();
+  CU(cudaStreamSynchronize(D->res_stream));
+  D->h_res->stop = 0;
+  D->res_live = false;
+  return B2_OK;
+}
+
 }  // namespace
 
 // =============================================================== C ABI =====
 extern "C" {
 
 static void submit_loop(Device *D);
+static int resident_setup(Device *D, uint32_t idle_us);
 
 const char *b2_last_error(void) { return g_err.c_str(); }
 int b2_abi_version(void) { return (int)B2_ABI_VERSION; }
@@ -421,15 +573,17 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
 
   D->qcap = queue_cap;
   D->succ_cap = queue_cap * 4u;
-  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_cells), (size_t)queue_cap * 8));
+  // three sets of cells: ordinary launches use the first, the resident worker alternates between the
+  // other two (at most two of its batches are in flight); epochs never mix between the two users
+  CU(cudaMalloc(reinterpret_cast<void **>(&D->d_cells), (size_t)queue_cap * 8 * 3));
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_head), 256));
   D->d_tail = D->d_head + 16;     // separate 64 B sectors
   D->d_cursor = D->d_head + 32;
   D->d_exited = D->d_head + 48;
   CU(cudaMalloc(reinterpret_cast<void **>(&D->d_fn), sizeof(FnEntry) * B2_MAX_FN));
   CU(cudaMemsetAsync(D->d_fn, 0, sizeof(FnEntry) * B2_MAX_FN, D->stream));
-  queue_init_kernel<<<(queue_cap + 255) / 256, 256, 0, D->stream>>>(D->d_cells, queue_cap,
-                                                                   D->d_head);
+  queue_init_kernel<<<(3 * queue_cap + 255) / 256, 256, 0, D->stream>>>(D->d_cells, 3 * queue_cap,
+                                                                       D->d_head);
   CU(cudaGetLastError());
   D->stats = b2_stats();
   D->stats.launches_other = 1;
@@ -524,6 +678,13 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
     D->q_stop = false;
     D->q_current = nullptr;
   }
+  D->res_enabled = false;
+  D->res_live = false;
+  D->compute_dirty = false;
+  if (env_int("B2_RESIDENT", 0) == 1) {
+    int rc = resident_setup(D, (uint32_t)std::max(0, env_int("B2_RESIDENT_IDLE_US", 0)));
+    if (rc) return rc;
+  }
   D->submitter = std::thread(submit_loop, D);
   D->up = true;
   return B2_OK;
@@ -547,9 +708,23 @@ int b2_shutdown(int dev) {
   std::lock_guard<std::mutex> lock_(D->mu);
   if (!D->up) return fail(B2_E_STATE, "device %d is not initialised", dev);
   cudaSetDevice(dev);
+  D->res_enabled = false;
+  resident_quiesce(D);
   cudaStreamSynchronize(D->upload);
   cudaStreamSynchronize(D->stream);
   cudaStreamSynchronize(D->egress);
+  if (D->d_ctl) {
+    cudaStreamDestroy(D->res_stream);
+    cudaFree(D->d_ctl);
+    cudaFreeHost(D->h_res);
+    for (auto &e : D->ring_ev)
+      if (e) { cudaEventDestroy(e); e = nullptr; }
+    D->d_ctl = nullptr;
+    D->h_res = D->d_res = nullptr;
+    D->h_ring = nullptr;
+    D->h_const = nullptr;
+    D->res_stream = nullptr;
+  }
   for (int i = 1; i < D->n_arenas; ++i)
     if (D->arena_ipc[i] && D->arena[i]) cudaIpcCloseMemHandle(D->arena[i]);
   for (auto &s : D->task_ring) staging_free(s);
@@ -611,6 +786,8 @@ int b2_get_stats(int dev, b2_stats *out) {
   if (!out) return fail(B2_E_ARG, "out is NULL");
   DEV_OR_FAIL(D, dev);
   *out = D->stats;
+  out->resident_instances = D->res_launches;
+  out->resident_batches = D->res_batches;
   return B2_OK;
 }
 
@@ -664,6 +841,7 @@ int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes) {
   if (!bytes) return B2_OK;
   CU(cudaMemcpyAsync(D->arena[0] + dev_off, D->h_in + host_off, bytes, cudaMemcpyHostToDevice,
                      D->stream));
+  D->compute_dirty = true;
   D->stats.bytes_h2d += bytes;
   return B2_OK;
 }
@@ -714,6 +892,7 @@ int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
     return fail(B2_E_ARG, "fill: device range outside arena");
   if (!bytes) return B2_OK;
   CU(cudaMemsetAsync(D->arena[0] + dev_off, byte_value, bytes, D->stream));
+  D->compute_dirty = true;
   return B2_OK;
 }
 
@@ -893,28 +1072,18 @@ static int record_ticket(Device *D, uint64_t *ticket) {
 // on the 12 x 4 KiB-stage kernel and claim several tickets per fetch-add.
 static int launch_worker(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32_t *d_status,
                          uint32_t n, uint32_t prefix, uint64_t operand_bytes) {
+  if (D->res_enabled && D->worker_tma) return resident_publish(D, d_tasks, d_succ, d_status, n, prefix, operand_bytes);
   WorkerArgs a;
-  memset(&a, 0, sizeof a);
+  fill_worker_consts(D, a);
   a.tasks = d_tasks;
   a.succ = d_succ;
   // status words live in the slot's own device buffer: the copy of batch k's statuses runs on
   // the egress stream while kernel k+1 (another slot) is already writing its own
   a.status = d_status;
-  a.fn_table = D->d_fn;
-  a.q.cells = D->d_cells;
-  a.q.head = D->d_head;
-  a.q.tail = D->d_tail;
   if (++D->epoch == 0) D->epoch = 1;
   a.q.epoch = D->epoch;
-  a.q.mask = D->qcap - 1;
-  a.cursor = D->d_cursor;
-  a.exited = D->d_exited;
   a.n_tasks = n;
   a.n_ready_prefix = prefix;
-  for (int i = 0; i < B2_MAX_ARENAS; ++i) {
-    a.arena[i] = D->arena[i];
-    a.arena_bytes[i] = D->arena_bytes[i];
-  }
   const uint64_t avg = n ? operand_bytes / n : 0;
   bool small = D->worker_tma && operand_bytes && avg <= 8192;
   if (D->worker_small_mode == 0) small = false;
@@ -1123,6 +1292,49 @@ int b2_table_destroy(int dev, uint32_t table_id) {
   return B2_OK;
 }
 
+// ---- resident worker ------------------------------------------------------------
+static int resident_setup(Device *D, uint32_t idle_us) {
+  int rc = load_stream_memops();
+  if (rc) return rc;
+  if (!D->worker_tma) return fail(B2_E_UNSUPPORTED, "the resident worker is the streaming worker (unset B2_WORKER=classic)");
+  if (!D->d_ctl) {
+    CU(cudaStreamCreateWithFlags(&D->res_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(reinterpret_cast<void **>(&D->d_ctl), sizeof(ResidentCtl)));
+    CU(cudaMemset(D->d_ctl, 0, sizeof(ResidentCtl)));
+    uint8_t *blk = nullptr;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&blk), 4096 + sizeof(ResidentBatch) * kResRing, cudaHostAllocMapped));
+    memset(blk, 0, 4096 + sizeof(ResidentBatch) * kResRing);
+    D->h_res = reinterpret_cast<ResidentHost *>(blk);
+    D->h_const = reinterpret_cast<uint32_t *>(blk + 1024);
+    D->h_ring = reinterpret_cast<ResidentBatch *>(blk + 4096);
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void **>(&D->d_res), D->h_res, 0));
+    CU(cudaFuncSetAttribute(worker_resident_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(worker_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kWorkerSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->res_ctas_per_sm, worker_resident_kernel, kCtaThreads,
+                                                     kWorkerSmemBytes));
+    if (D->res_ctas_per_sm < 1) return fail(B2_E_UNSUPPORTED, "the resident worker does not fit on an SM");
+    D->res_ctas_per_sm = std::min(D->res_ctas_per_sm, std::max(1, D->worker_ctas_per_sm));
+    D->res_submitted = 0;
+    D->res_instance = 0;
+  }
+  if (idle_us) D->res_idle_us = idle_us;
+  D->res_life_ms = (uint32_t)std::max(100, env_int("B2_RESIDENT_LIFE_MS", 2000));
+  D->res_enabled = true;
+  return B2_OK;
+}
+
+int b2_resident_enable(int dev, uint32_t idle_us) {
+  DEV_ORDERED(D, dev);
+  return resident_setup(D, idle_us);
+}
+
+int b2_resident_disable(int dev) {
+  DEV_ORDERED(D, dev);
+  D->res_enabled = false;
+  return resident_quiesce(D);
+}
+
 int b2_mark(int dev, uint64_t *ticket) {
   DEV_ORDERED(D, dev);
   return record_ticket(D, ticket);
@@ -1173,6 +1385,16 @@ int b2_wait(int dev, uint64_t ticket) {
     CU(cudaSetDevice(dev));
   }
   // Block outside the device lock so other threads can keep submitting.
+  Device *D = get(dev);
+  if (D->h_res && D->h_res->error) {
+    // a resident instance hit its lifetime cap while a submitted batch had not arrived: nothing
+    // will ever release the streams waiting for it — say so instead of blocking forever
+    for (int spins = 0; cudaEventQuery(ev) == cudaErrorNotReady; ++spins) {
+      if (spins > 20000) return fail(B2_E_CUDA, "resident worker left with a submitted batch pending (lifetime cap)");
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+    return B2_OK;
+  }
   CU(cudaEventSynchronize(ev));
   return B2_OK;
 }
@@ -1320,8 +1542,9 @@ static void submit_one(Device *D, Submission &sub) {
         rc = fail(B2_E_ARG, "b2_submit: ingress range [%llu, +%llu) out of bounds",
                   (unsigned long long)b.in_off, (unsigned long long)b.in_bytes);
       else {
+        // resident worker: the payload travels on the upload stream, in front of the table and the doorbell
         cu(cudaMemcpyAsync(D->arena[0] + b.in_off, D->h_in + b.in_off, b.in_bytes,
-                           cudaMemcpyHostToDevice, D->stream), "cudaMemcpyAsync(H2D)");
+                           cudaMemcpyHostToDevice, D->res_enabled ? D->upload : D->stream), "cudaMemcpyAsync(H2D)");
         D->stats.bytes_h2d += b.in_bytes;
       }
     }
@@ -1494,6 +1717,7 @@ int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_
   if (!bytes) return B2_OK;
   CU(cudaMemcpyAsync(D->arena[dst_arena_id] + dst_off, D->arena[0] + src_off, bytes,
                      cudaMemcpyDefault, D->stream));
+  D->compute_dirty = true;
   return B2_OK;
 }
 
@@ -1540,6 +1764,7 @@ int b2_flush_l2(int dev, uint64_t scratch_off, uint64_t bytes) {
   if (scratch_off + bytes > D->arena_bytes[0]) return fail(B2_E_ARG, "flush range outside arena");
   static int v = 0;
   CU(cudaMemsetAsync(D->arena[0] + scratch_off, (++v) & 0xff, bytes, D->stream));
+  D->compute_dirty = true;
   return B2_OK;
 }
 

@@ -175,6 +175,8 @@ typedef struct b2_stats {
   uint64_t bytes_packed;      /* sum of span bytes moved                      */
   uint64_t bytes_h2d;
   uint64_t bytes_d2h;
+  uint64_t resident_instances;  /* resident-worker kernel instances launched (b2_resident_enable) */
+  uint64_t resident_batches;    /* batches published to a resident worker through the doorbell     */
 } b2_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -276,6 +278,20 @@ int b2_table_create(int dev, const b2_task *tasks, uint32_t n, const uint32_t *s
                     uint32_t *table_id);
 int b2_table_launch(int dev, uint32_t table_id, uint64_t status_host_off, uint64_t *ticket);
 int b2_table_destroy(int dev, uint32_t table_id);
+/* Resident worker: with this on, the worker kernel is launched ONCE and stays on the GPU across
+ * batches (north_star: "a persistent per-GPU worker kernel that pulls task descriptors from a
+ * device-side MPMC queue").  b2_launch / b2_submit / b2_table_launch then publish their batch
+ * through a descriptor ring in device memory — table, payload and ring entry travel on the upload
+ * stream, followed by a stream-ordered write of the doorbell word; completion is a word the other
+ * streams wait on — instead of launching a kernel per batch, so consecutive batches run with no
+ * launch gap and overlap tail-to-head.  The instance leaves by itself after idle_us microseconds
+ * without a published batch (0 = keep the current setting, default 200; a Dekker handshake over
+ * two words of mapped pinned memory makes "leave" and "a batch is being submitted" mutually
+ * visible), and a later batch simply starts a new instance: the SMs are never held while there is
+ * nothing to do, so other kernels of the process (the span mover, NCCL) cannot deadlock behind it.
+ * Also switched on by B2_RESIDENT=1 at b2_init. */
+int b2_resident_enable(int dev, uint32_t idle_us);
+int b2_resident_disable(int dev);
 /* Records a completion ticket after whatever has been queued so far. */
 int b2_mark(int dev, uint64_t *ticket);
 int b2_poll(int dev, uint64_t ticket);          /* B2_OK | B2_E_NOTREADY  (ssh.py:388-406) */

@@ -289,6 +289,12 @@ class FakeLib:
         tabs[table_id] = None
         return 0
 
+    def b2_resident_enable(self, dev, idle_us):
+        return 0          # the numpy model has no launch gaps to hide
+
+    def b2_resident_disable(self, dev):
+        return 0
+
     def b2_cancel(self, dev, ticket, first, count):
         self.cancels = getattr(self, "cancels", []) + [(dev, ticket, first, count)]
         return 0          # the fake runs a batch inside b2_submit: nothing is left to tombstone
