@@ -178,8 +178,8 @@ async def _verify(python_path: str, conda_env: str) -> str:
         if code != 0:
             message = err.strip() or f"No conda environment named {conda_env} found on remote machine."
     if not message:
-        out, err, _ = await _shell(f"{_conda_prefix(conda_env)}{python_path} --version")
-        if "3" not in (out + err).strip():          # python 2 prints its version on stderr
+        out, _, _ = await _shell(f"{_conda_prefix(conda_env)}{python_path} --version")
+        if "3" not in out.strip():                  # the reference's test, on stdout only (ssh.py:521-522)
             message = "No Python 3 installation found on remote machine localhost"
     _verified[key] = message
     return message
