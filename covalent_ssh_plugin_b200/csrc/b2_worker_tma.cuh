@@ -67,7 +67,10 @@ struct StageHdr {
   uint32_t status;           // kHdrFailed: the status to report
   float alpha, beta;
   uint32_t succ_begin, succ_count;
+  uint32_t owner;            // warp mode: the worker warp that consumes this stage (kOwnerAll: every warp)
+  uint32_t pad;
 };
+constexpr uint32_t kOwnerAll = 0xFFu;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -155,7 +158,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-template <int kStages, uint32_t kTileBytes, bool kResident>
+// kWarpMode (small-payload flavour): a streaming electron is consumed by ONE worker warp — stages are
+// dealt to the eight warps round-robin, per electron — instead of by all 256 worker threads.  An
+// electron of a few KiB is 64-256 vectors: spread over 256 threads it costs eight warps a barrier
+// round trip, a status hand-off and ~100 instructions each; owned by one warp it costs that once, the
+// other seven only look at the stage header and hand the stage back.  CTA-wide work (SUM, STACK_SUM,
+// integer electrons, batch markers) is still done by all warps together.
+template <int kStages, uint32_t kTileBytes, bool kResident, bool kWarpMode>
 __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const ResidentArgs &ra) {
   extern __shared__ __align__(128) uint8_t stage_mem[];   // kStages x kTileBytes, dynamic
   __shared__ StageHdr hdr[kStages];
@@ -192,10 +201,12 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
       auto marker = [&](uint32_t kind, const BatchView *v) {
         const uint32_t s = acquire();
         hdr[s].kind = kind;
+        hdr[s].owner = kOwnerAll;
         if (v) bview[s] = *v;
         mbar_arrive(smem_addr(&full_bar[s]));
         ++it;
       };
+      uint32_t deal = 0;   // warp mode: next warp to be dealt an electron
 
       // Streams every electron this CTA claims from batch v (tickets in increasing order).
       auto produce = [&](const BatchView &v) {
@@ -251,6 +262,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             StageHdr &h = hdr[s];
             h.kind = kHdrFailed;
             h.status = B2_TS_CANCELLED;
+            h.owner = kWarpMode ? (deal++ % kWorkerWarps) : kOwnerAll;
             h.task = ti;
             h.last = 1;
             h.succ_begin = t.succ_begin;
@@ -268,6 +280,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             h.last = 1;
             h.succ_begin = t.succ_begin;
             h.succ_count = t.succ_count;
+            h.owner = kOwnerAll;
             if (kind == B2_K__COUNT) {
               h.kind = kHdrFailed;
               h.status = B2_TS_BAD_FN;
@@ -296,6 +309,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             StageHdr &h = hdr[s];
             h.kind = kHdrFailed;
             h.status = B2_TS_BAD_ARG;
+            h.owner = kOwnerAll;
             h.task = ti;
             h.last = 1;
             h.succ_begin = t.succ_begin;
@@ -305,6 +319,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             continue;
           }
           const uint32_t per_tile = two ? kTileBytes / 2 : kTileBytes;
+          const uint32_t owner = kWarpMode ? (deal++ % kWorkerWarps) : kOwnerAll;   // every tile of it
           uint64_t off = 0;
           do {
             const uint64_t left = bytes - off;
@@ -319,6 +334,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             h.n_vec = b16 >> 4;
             h.tail_bytes = chunk - b16;
             h.kind = kind;
+            h.owner = owner;
             h.last = last ? 1u : 0u;
             h.task = ti;
             h.alpha = fn.alpha;
@@ -493,6 +509,15 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
         if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
         continue;
       }
+      const uint32_t owner = kWarpMode ? h.owner : kOwnerAll;
+      if (kWarpMode && owner != kOwnerAll && owner != (uint32_t)(threadIdx.x >> 5)) {
+        __syncwarp();                                   // somebody else's electron: hand the stage back
+        if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
+        continue;
+      }
+      const bool solo = kWarpMode && owner != kOwnerAll;   // this warp alone runs the electron
+      const uint32_t tid = solo ? (uint32_t)lane : threadIdx.x;
+      const uint32_t nthr = solo ? (uint32_t)kWarp : (uint32_t)kWorkerThreads;
       uint32_t status = B2_TS_OK;
       if (kind == kHdrFailed) {
         status = h.status;
@@ -527,7 +552,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
         int4 *o = reinterpret_cast<int4 *>(h.out);
         const uint32_t n = h.n_vec;
         const float al = h.alpha, be = h.beta;
-        for (uint32_t i = threadIdx.x; i < n; i += kWorkerThreads) {
+        for (uint32_t i = tid; i < n; i += nthr) {
           int4 v = x[i];
           if (kind != B2_K_COPY) {
             float4 f = *reinterpret_cast<float4 *>(&v);
@@ -554,33 +579,38 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
         }
         // < 16 trailing bytes of the electron: read from global, element by element
         const uint32_t tb = h.tail_bytes;
-        if (tb && threadIdx.x < (kind == B2_K_COPY ? tb : tb / 4)) {
+        if (tb && tid < (kind == B2_K_COPY ? tb : tb / 4)) {
           uint8_t *ot = h.out + (n << 4);
           if (kind == B2_K_COPY) {
-            ot[threadIdx.x] = h.tail0[threadIdx.x];
+            ot[tid] = h.tail0[tid];
           } else {
-            const float xv = reinterpret_cast<const float *>(h.tail0)[threadIdx.x];
+            const float xv = reinterpret_cast<const float *>(h.tail0)[tid];
             float r;
             if (kind == B2_K_SCALE_ADD) {
               r = __fadd_rn(__fmul_rn(al, xv), be);
             } else {
-              const float yv = reinterpret_cast<const float *>(h.tail1)[threadIdx.x];
+              const float yv = reinterpret_cast<const float *>(h.tail1)[tid];
               r = (kind == B2_K_ADD) ? __fadd_rn(xv, yv)
                   : (kind == B2_K_MUL) ? __fmul_rn(xv, yv)
                                        : __fadd_rn(__fmul_rn(al, xv), yv);
             }
-            reinterpret_cast<float *>(ot)[threadIdx.x] = r;
+            reinterpret_cast<float *>(ot)[tid] = r;
           }
         }
       }
 
       if (h.last) {
         const uint32_t ti = h.task, succ_begin = h.succ_begin, succ_count = h.succ_count;
-        if (threadIdx.x == 0) s_status = status;
-        worker_sync();  // every result store of this electron is ordered before what follows
-        if (threadIdx.x == 0) wv.status[ti] = s_status;
-        for (uint32_t base = 0; base < succ_count; base += kWorkerThreads) {
-          const uint32_t e = base + threadIdx.x;
+        if (solo) {
+          __syncwarp();   // the warp's result stores of this electron are ordered before what follows
+          if (lane == 0) wv.status[ti] = status;
+        } else {
+          if (threadIdx.x == 0) s_status = status;
+          worker_sync();  // every result store of this electron is ordered before what follows
+          if (threadIdx.x == 0) wv.status[ti] = s_status;
+        }
+        for (uint32_t base = 0; base < succ_count; base += nthr) {
+          const uint32_t e = base + tid;
           bool fire = false;
           uint32_t sidx = 0;
           if (e < succ_count) {
@@ -614,12 +644,12 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
 
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_kernel(const __grid_constant__ WorkerArgs a) {
-  worker_tma_body<kStages, kTileBytes, false>(a, ResidentArgs{});
+  worker_tma_body<kStages, kTileBytes, false, false>(a, ResidentArgs{});
 }
 
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_small_kernel(const __grid_constant__ WorkerArgs a) {
-  worker_tma_body<kSmallStages, kSmallTileBytes, false>(a, ResidentArgs{});
+  worker_tma_body<kSmallStages, kSmallTileBytes, false, true>(a, ResidentArgs{});
 }
 
 // The resident worker: one CTA set that outlives its batches (b2_resident_enable).  `a` supplies
@@ -627,7 +657,7 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
 // everything per batch comes through the ring in `ra.ctl`.
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_resident_kernel(const __grid_constant__ WorkerArgs a, const __grid_constant__ ResidentArgs ra) {
-  worker_tma_body<kStages, kTileBytes, true>(a, ra);
+  worker_tma_body<kStages, kTileBytes, true, false>(a, ra);
 }
 
 }  // namespace b2
