@@ -26,7 +26,7 @@ BATCH_INDEPENDENT = 0x1
 F_ARENA0_SHIFT, F_ARENA1_SHIFT, F_ARENAO_SHIFT = 8, 12, 16
 NO_STATUS_COPY = 0xFFFFFFFFFFFFFFFF
 MAX_FN = 1024
-MAX_ARENAS = 9
+MAX_ARENAS = 16
 ABI_VERSION = 2
 
 

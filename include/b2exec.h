@@ -95,7 +95,7 @@ enum b2_kind {
 #define B2_F_ARENA1_SHIFT 12    /* bits 12..15: arena id of arg1               */
 #define B2_F_ARENAO_SHIFT 16    /* bits 16..19: arena id of out                */
 #define B2_NO_SUCC 0xFFFFFFFFu
-#define B2_MAX_ARENAS 9         /* local + 8 peers                             */
+#define B2_MAX_ARENAS 16        /* local + 15 mapped peers (4-bit arena id): same-process and IPC mappings of the same GPU count separately */
 #define B2_MAX_FN 1024          /* callback-table capacity                     */
 
 /*
