@@ -360,7 +360,10 @@ def run_cuda_arm(args, dist: Dist):
     n, payload = args.electrons, args.payload
     count = payload // 4
     total = n * payload
-    max_batch = env_int("B2_MAX_BATCH", 1024)
+    # electrons per b2_submit: 256 x 64 KiB = 16 MiB per batch keeps the copy / H2D / D2H pipeline busy while the
+    # event loop is still staging, and keeps the last batch (pure latency) short; measured flat from 256 to 2048 at
+    # 10 000 electrons per dispatcher, 30 % better than 1024 at the 1 250 per dispatcher of the 8-GPU lattice
+    max_batch = env_int("B2_MAX_BATCH", 256)
     dev_batch = min(n, 1 << 16)     # device-resident operands need no staging pipeline: one launch per step,
                                     # as engine.run_dag / a lattice level issues it (queue capacity 65 536)
     per_seg, n_seg, n_out = engine_shape(n, payload, max_batch)
@@ -571,27 +574,30 @@ def run_cuda_arm(args, dist: Dist):
     def checksum(out):
         return sum(float(r[j]) for r in out for j in probe)
 
-    e2e_steps = max(1, min(args.steps, 10))
-    out = asyncio.run(lattice_step("check"))
-    for k, i in enumerate(mine[:: max(1, len(mine) // 50)]):
+    e2e_steps = max(1, args.steps)                       # exactly the K steps the caller asked for
+    loop = asyncio.new_event_loop()                      # ONE event loop for all steps, like a dispatcher's
+    run_step = loop.run_until_complete
+    out = run_step(lattice_step("check"))
+    for i in mine[:: max(1, len(mine) // 50)]:
         kk = mine.index(i)
         assert np.array_equal(out[kk], np.float32(2.0) * xs[i] + np.float32(1.0)), "e2e result differs from numpy"
     del out
-    for w in range(max(1, min(args.warmup, 3))):
-        asyncio.run(lattice_step(f"w{w}"))
+    for w in range(args.warmup):                          # W untimed passes (>= 3), after the correctness pass above
+        run_step(lattice_step(f"w{w}"))
     L.call("b2_sync", dev)
     dist.barrier()
     c0, st0 = dict(eng.counters), eng.stats()
     verified = True
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        out = asyncio.run(lattice_step(f"s{s}"))
+        out = run_step(lattice_step(f"s{s}"))
         verified = verified and abs(checksum(out) - want_sum) <= 1e-9 * max(1.0, abs(want_sum))
         del out
     L.call("b2_sync", dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     c1, st1 = dict(eng.counters), eng.stats()
     dist.barrier()
+    loop.close()
     e2e_ranks = dist.gather(e2e_s)
     e2e_s = max(e2e_ranks)
     verified = dist.all_true(verified)
@@ -625,18 +631,21 @@ def run_cuda_arm(args, dist: Dist):
                     exs[i % world].run(electrons.scale_add, [xall[i]], {}, {"dispatch_id": tag, "node_id": i})
                     for i in range(n)])
 
+            sloop = asyncio.new_event_loop()
             for w in range(2):
-                asyncio.run(single_step(f"sw{w}"))
+                sloop.run_until_complete(single_step(f"sw{w}"))
             ok = True
+            sd_steps = max(3, min(e2e_steps, 10))
             t0 = time.perf_counter()
-            for s in range(e2e_steps):
-                out = asyncio.run(single_step(f"ss{s}"))
+            for s in range(sd_steps):
+                out = sloop.run_until_complete(single_step(f"ss{s}"))
                 ok = ok and abs(checksum(out) - want_all) <= 1e-9 * max(1.0, abs(want_all))
                 del out
             for d in range(world):
                 L.call("b2_sync", d)
-            dt = (time.perf_counter() - t0) / e2e_steps
-            single = {"value": n / dt, "unit": "electrons/s", "ms_per_step": 1e3 * dt, "steps": e2e_steps,
+            dt = (time.perf_counter() - t0) / sd_steps
+            sloop.close()
+            single = {"value": n / dt, "unit": "electrons/s", "ms_per_step": 1e3 * dt, "steps": sd_steps,
                       "gpus_driven": world, "verified": ok,
                       "what": f"one process, one asyncio loop, {world} executors cuda:0..{world - 1}, electron i -> GPU i mod {world}"}
             del xall

@@ -59,7 +59,7 @@ MiB = 1 << 20
 DEFAULTS = {
     "arena_bytes": int(os.environ.get("B2_ARENA_BYTES", 4096 * MiB)),
     "staging_bytes": int(os.environ.get("B2_STAGING_BYTES", 1024 * MiB)),
-    "n_segments": int(os.environ.get("B2_SEGMENTS", 8)),
+    "n_segments": int(os.environ.get("B2_SEGMENTS", 32)),      # 32 MiB per batch each way by default
     "n_out_segments": int(os.environ.get("B2_OUT_SEGMENTS", 0)) or None,   # default: same as n_segments
     "max_batch": int(os.environ.get("B2_MAX_BATCH", 4096)),
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
