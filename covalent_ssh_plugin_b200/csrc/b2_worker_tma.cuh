@@ -99,7 +99,7 @@ struct BatchView {
 constexpr uint32_t kResRing = 64;            // batches that may be published ahead of the worker
 constexpr uint32_t kResNone = 0xFFFFFFFFu;
 
-struct ResidentBatch {     // one ring entry (device memory, written by the host through the upload stream)
+struct ResidentBatch {     // one ring entry: written by the host into mapped pinned memory, mirrored into ctl->ring by the leader
   b2_task *tasks;
   const uint32_t *succ;
   uint32_t *status;
@@ -126,6 +126,9 @@ struct ResidentHost {      // mapped pinned host memory: the two words of the ex
   volatile uint32_t stop;        // host -> kernel: leave as soon as nothing submitted is pending
   volatile uint32_t state;       // kernel -> host: (instance << 2) | 1 running | 2 leaving
   volatile uint32_t error;       // kernel -> host: 1 = a submitted batch never arrived (lifetime cap hit)
+  volatile uint32_t done;        // kernel -> host: batches completed (the host may reuse ring entries below it)
+  uint32_t pad[11];
+  ResidentBatch ring[kResRing];  // host -> kernel: batch descriptors, plain CPU stores before the doorbell is rung
 };
 struct ResidentArgs {
   ResidentCtl *ctl;
@@ -392,6 +395,13 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
                 // at most two batches are in flight (two sets of queue cells): b starts once b-2 is done
                 const uint32_t dn = ld_acquire_gpu_u32(&ctl->done);
                 if ((int32_t)(b - dn) <= 1) {
+                  // The descriptor sits in mapped host memory (the host wrote it with ordinary stores
+                  // before it rang the doorbell): one 64-byte read over PCIe by the leader, mirrored
+                  // into device memory for everybody else.
+                  const volatile uint64_t *src = reinterpret_cast<const volatile uint64_t *>(&ra.host->ring[b % kResRing]);
+                  uint64_t *dst = reinterpret_cast<uint64_t *>(&ctl->ring[b % kResRing]);
+#pragma unroll
+                  for (int w = 0; w < (int)(sizeof(ResidentBatch) / 8); ++w) dst[w] = src[w];
                   st_release_gpu_u32(&ctl->approved, b + 1);
                   break;
                 }
@@ -503,6 +513,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             *wv.finished = 0;
             __threadfence_system();
             st_release_sys_u32(&ra.ctl->done, wv.seq + 1u);
+            ra.host->done = wv.seq + 1u;
           }
         }
         __syncwarp();

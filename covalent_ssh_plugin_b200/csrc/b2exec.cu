@@ -141,9 +141,7 @@ struct Device {
   cudaStream_t res_stream = nullptr;
   ResidentCtl *d_ctl = nullptr;
   ResidentHost *h_res = nullptr, *d_res = nullptr;   // mapped pinned block: host / device address
-  ResidentBatch *h_ring = nullptr;                   // pinned source of the ring entries
   uint32_t *h_const = nullptr;                       // pinned constants for stream-ordered word writes
-  cudaEvent_t ring_ev[kResRing] = {};
   uint32_t res_submitted = 0;      // sequence number of the next batch
   uint32_t res_instance = 0;
   uint32_t res_idle_us = 200, res_life_ms = 2000;
@@ -444,15 +442,19 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
                      uint32_t prefix, uint64_t operand_bytes) {
   const uint32_t seq = D->res_submitted;
   const uint32_t slot = seq % kResRing;
-  if (D->ring_ev[slot]) CU(cudaEventSynchronize(D->ring_ev[slot]));   // the slot's previous upload has left pinned memory
-  else CU(cudaEventCreateWithFlags(&D->ring_ev[slot], cudaEventDisableTiming));
+  // the ring entry being replaced belongs to batch seq - kResRing: wait (on the host) until it is done.
+  // Only a producer that runs a whole ring ahead of the GPU ever waits here.
+  for (int spins = 0; seq >= kResRing && (int32_t)(D->h_res->done - (seq - kResRing + 1)) < 0; ++spins) {
+    if (D->h_res->error || spins > 4000000) return fail(B2_E_CUDA, "resident worker stopped consuming batches");
+    if (spins > 64) std::this_thread::yield();
+  }
   const uint64_t avg = n ? operand_bytes / n : 0;
   const int grid = D->sm_count * std::max(1, D->res_ctas_per_sm);
   uint32_t k = 1;
   if (operand_bytes) k = avg <= 2048 ? 8u : avg <= 8192 ? 4u : avg <= 32768 ? 2u : 1u;
   while (k > 1 && (uint64_t)grid * k * 4 > n) k >>= 1;
   if (D->claim_k_override > 0) k = (uint32_t)D->claim_k_override;
-  ResidentBatch &rb = D->h_ring[slot];
+  ResidentBatch rb;
   memset(&rb, 0, sizeof rb);
   rb.tasks = d_tasks;
   rb.succ = d_succ;
@@ -460,6 +462,7 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
   rb.n_tasks = n;
   rb.prefix = prefix;
   rb.claim_k = k;
+  memcpy(const_cast<ResidentBatch *>(&D->h_res->ring[slot]), &rb, sizeof rb);   // plain stores; visible before the doorbell
   // exit handshake, host half: announce the batch BEFORE any of its stream operations, then look
   // at the kernel's state.  If the instance we launched last is leaving, queue another one behind it.
   D->h_res->submitted = seq + 1;
@@ -474,10 +477,6 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
     CU(cudaStreamWaitEvent(D->upload, D->to_egress, 0));
     D->compute_dirty = false;
   }
-  if (seq >= kResRing)      // the ring entry being replaced belongs to a batch that must have completed
-    CUD(g_wait32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->done, seq - kResRing + 1, CU_STREAM_WAIT_VALUE_GEQ));
-  CU(cudaMemcpyAsync(&D->d_ctl->ring[slot], &rb, sizeof rb, cudaMemcpyHostToDevice, D->upload));
-  CU(cudaEventRecord(D->ring_ev[slot], D->upload));
   CUD(g_write32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->doorbell, seq + 1, CU_STREAM_WRITE_VALUE_DEFAULT));
   // everything queued on the compute stream after this point is ordered after the batch: the
   // existing egress / ticket logic (events recorded on the compute stream) needs no other change
@@ -717,11 +716,8 @@ int b2_shutdown(int dev) {
     cudaStreamDestroy(D->res_stream);
     cudaFree(D->d_ctl);
     cudaFreeHost(D->h_res);
-    for (auto &e : D->ring_ev)
-      if (e) { cudaEventDestroy(e); e = nullptr; }
     D->d_ctl = nullptr;
     D->h_res = D->d_res = nullptr;
-    D->h_ring = nullptr;
     D->h_const = nullptr;
     D->res_stream = nullptr;
   }
@@ -1127,8 +1123,10 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   if (D->pend_succ)
     CU(cudaMemcpyAsync(s.d + succ_off, s.h + succ_off, (size_t)D->pend_succ * 4,
                        cudaMemcpyHostToDevice, D->upload));
-  CU(cudaEventRecord(s.up, D->upload));
-  CU(cudaStreamWaitEvent(D->stream, s.up, 0));
+  if (!(D->res_enabled && D->worker_tma)) {   // resident worker: the doorbell follows the table on the upload stream
+    CU(cudaEventRecord(s.up, D->upload));
+    CU(cudaStreamWaitEvent(D->stream, s.up, 0));
+  }
 
   uint32_t *slot_status = reinterpret_cast<uint32_t *>(s.d + succ_off + (size_t)D->succ_cap * 4);
   {
@@ -1302,11 +1300,11 @@ static int resident_setup(Device *D, uint32_t idle_us) {
     CU(cudaMalloc(reinterpret_cast<void **>(&D->d_ctl), sizeof(ResidentCtl)));
     CU(cudaMemset(D->d_ctl, 0, sizeof(ResidentCtl)));
     uint8_t *blk = nullptr;
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&blk), 4096 + sizeof(ResidentBatch) * kResRing, cudaHostAllocMapped));
-    memset(blk, 0, 4096 + sizeof(ResidentBatch) * kResRing);
+    const size_t blk_bytes = ((sizeof(ResidentHost) + 255) & ~size_t(255)) + 256;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&blk), blk_bytes, cudaHostAllocMapped));
+    memset(blk, 0, blk_bytes);
     D->h_res = reinterpret_cast<ResidentHost *>(blk);
-    D->h_const = reinterpret_cast<uint32_t *>(blk + 1024);
-    D->h_ring = reinterpret_cast<ResidentBatch *>(blk + 4096);
+    D->h_const = reinterpret_cast<uint32_t *>(blk + blk_bytes - 256);
     CU(cudaHostGetDevicePointer(reinterpret_cast<void **>(&D->d_res), D->h_res, 0));
     CU(cudaFuncSetAttribute(worker_resident_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(worker_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
