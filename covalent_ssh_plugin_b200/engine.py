@@ -112,7 +112,7 @@ class Batch:
 
     __slots__ = ("engine", "seg", "oseg", "n", "n_jobs", "in_used", "out_used", "table", "table_mem", "loop",
                  "ticket", "unread", "done", "flushed", "error", "lease", "zero_copy", "out_freed",
-                 "waiters", "keep", "all_ok", "f32", "in_base", "out_base", "future")
+                 "waiters", "keep", "all_ok", "f32", "in_base", "out_base")
 
     def __init__(self, engine: "DeviceEngine", seg: int, oseg: int, loop):
         self.engine = engine
@@ -139,7 +139,6 @@ class Batch:
         self.keep: list = []        # operand objects the queued copy jobs still read from
         self.all_ok = False         # every status word of the batch is B2_TS_OK (set on completion)
         self.f32 = None             # float32 view of the egress segment (zero-copy results are slices of it)
-        self.future = None          # legacy: completed together with the waiters (tests await it)
 
 
 class Staged:
