@@ -161,6 +161,220 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// ---- cooperative producer (small-payload flavour) ------------------------------------------
+// With electrons of a few KiB the single producer THREAD is the limiter: ~150 dependent instructions
+// per electron (record, callback entry, bounds, header, expect_tx, bulk copy) at one warp's issue
+// rate is ~1 us, however fast the workers are.  Here the producer WARP shares the work: a claim of K
+// ready-at-submit tickets is handled by K lanes at once — each lane reads its own task record, plans
+// its electron, an exclusive scan over the lanes' stage counts hands every lane its range of the
+// stage ring, and each lane fills its own stages (it waits only on the ring slots it was dealt, so
+// the lanes make progress independently).  Claims that touch released dependents (tickets >= the
+// ready prefix) or the end of the table are walked by lane 0 alone, in ticket order.
+struct ElectronPlan {
+  FnEntry fn;
+  const uint8_t *p0, *p1;
+  uint8_t *po;
+  uint64_t bytes;
+  uint32_t kind;      // validated b2_kind, or B2_K__COUNT
+  uint32_t mode;      // 0: streams through the ring, 1: one "legacy" stage, 2: status only
+  uint32_t status;    // mode 2
+  uint32_t need;      // stages it occupies
+  bool two;
+};
+
+template <uint32_t kTileBytes>
+__device__ __forceinline__ ElectronPlan plan_electron(const WorkerArgs &a, const b2_task &t) {
+  ElectronPlan c;
+  c.fn.kind = 0; c.fn.alpha = 0.f; c.fn.beta = 0.f; c.fn.pad = 0; c.fn.ialpha = 0; c.fn.ibeta = 0;
+  c.p0 = c.p1 = nullptr;
+  c.po = nullptr;
+  c.bytes = 0;
+  c.two = false;
+  c.need = 1;
+  c.status = B2_TS_OK;
+  uint32_t kind = B2_K__COUNT;
+  if (t.fn_id < B2_MAX_FN) {
+    c.fn = a.fn_table[t.fn_id];
+    kind = c.fn.kind;
+    if (kind >= B2_K__COUNT || (kind == B2_K_NONE && t.fn_id != 0)) kind = B2_K__COUNT;
+  }
+  c.kind = kind;
+  if (t.flags & B2_F_CANCELLED) { c.mode = 2; c.status = B2_TS_CANCELLED; return c; }
+  if (kind == B2_K__COUNT) { c.mode = 2; c.status = B2_TS_BAD_FN; return c; }
+  if (!is_streaming_kind(kind)) { c.mode = 1; return c; }
+  c.two = (kind == B2_K_ADD || kind == B2_K_MUL || kind == B2_K_AXPY);
+  c.bytes = (kind == B2_K_COPY) ? t.count : t.count * 4;
+  bool ok = true;
+  c.p0 = resolve(a, (t.flags >> B2_F_ARENA0_SHIFT) & 15u, t.arg0, c.bytes, &ok);
+  c.p1 = c.two ? resolve(a, (t.flags >> B2_F_ARENA1_SHIFT) & 15u, t.arg1, c.bytes, &ok) : nullptr;
+  c.po = resolve(a, (t.flags >> B2_F_ARENAO_SHIFT) & 15u, t.out, c.bytes, &ok);
+  if ((t.flags & (B2_F_IMM0 | (c.two ? B2_F_IMM1 : 0u))) || !ok || !aligned16(c.p0) || !aligned16(c.po) ||
+      (c.two && !aligned16(c.p1))) {
+    c.mode = 2;
+    c.status = B2_TS_BAD_ARG;
+    return c;
+  }
+  c.mode = 0;
+  const uint32_t per_tile = c.two ? kTileBytes / 2 : kTileBytes;
+  c.need = c.bytes ? (uint32_t)((c.bytes + per_tile - 1) / per_tile) : 1u;
+  return c;
+}
+
+template <int kStages, uint32_t kTileBytes>
+__device__ __forceinline__ void coop_producer(const WorkerArgs &a, StageHdr *hdr, Slot *legacy, BatchView *bview,
+                                              unsigned long long *full_bar, unsigned long long *empty_bar,
+                                              uint8_t *stage_mem) {
+  const uint32_t lane = threadIdx.x & 31u;
+  constexpr uint32_t kWorkerWarps = kWorkerThreads / kWarp;
+  constexpr unsigned kFull = 0xffffffffu;
+  uint32_t it = 0, deal = 0;   // identical in every lane at the warp-synchronous points
+
+  auto acquire_at = [&](uint32_t i) -> uint32_t {
+    const uint32_t s = i % kStages;
+    const uint32_t use = i / kStages;
+    if (use >= 1) mbar_wait(smem_addr(&empty_bar[s]), (use - 1) & 1u);
+    return s;
+  };
+  // fills the stages [i0, i0 + c.need) for one electron
+  auto emit = [&](const b2_task &t, uint32_t ti, const ElectronPlan &c, uint32_t i0, uint32_t owner) {
+    if (c.mode != 0) {
+      const uint32_t s = acquire_at(i0);
+      StageHdr &h = hdr[s];
+      h.task = ti;
+      h.last = 1;
+      h.succ_begin = t.succ_begin;
+      h.succ_count = t.succ_count;
+      if (c.mode == 2) {
+        h.kind = kHdrFailed;
+        h.status = c.status;
+        h.owner = owner;
+      } else {
+        h.kind = kHdrLegacy;
+        h.owner = kOwnerAll;
+        legacy[s].t = t;
+        legacy[s].fn = c.fn;
+        legacy[s].index = ti;
+        legacy[s].kind = c.kind;
+      }
+      mbar_arrive(smem_addr(&full_bar[s]));
+      return;
+    }
+    const uint32_t per_tile = c.two ? kTileBytes / 2 : kTileBytes;
+    uint64_t off = 0;
+    uint32_t i = i0;
+    do {
+      const uint64_t left = c.bytes - off;
+      const uint32_t chunk = left < per_tile ? (uint32_t)left : per_tile;
+      const bool last = (off + chunk == c.bytes);
+      const uint32_t b16 = chunk & ~15u;
+      const uint32_t s = acquire_at(i);
+      StageHdr &h = hdr[s];
+      h.out = c.po + off;
+      h.tail0 = c.p0 + off + b16;
+      h.tail1 = c.two ? c.p1 + off + b16 : nullptr;
+      h.n_vec = b16 >> 4;
+      h.tail_bytes = chunk - b16;
+      h.kind = c.kind;
+      h.owner = owner;
+      h.last = last ? 1u : 0u;
+      h.task = ti;
+      h.alpha = c.fn.alpha;
+      h.beta = c.fn.beta;
+      h.succ_begin = t.succ_begin;
+      h.succ_count = t.succ_count;
+      const uint32_t fb = smem_addr(&full_bar[s]);
+      if (b16) {
+        const uint32_t dst = smem_addr(stage_mem) + s * kTileBytes;
+        mbar_expect_tx(fb, c.two ? 2 * b16 : b16);
+        bulk_g2s(dst, c.p0 + off, b16, fb);
+        if (c.two) bulk_g2s(dst + kTileBytes / 2, c.p1 + off, b16, fb);
+      } else {
+        mbar_arrive(fb);
+      }
+      ++i;
+      off += chunk;
+    } while (off < c.bytes);
+  };
+
+  BatchView v;
+  v.tasks = a.tasks;
+  v.succ = a.succ;
+  v.status = a.status;
+  v.q = a.q;
+  v.cursor = a.cursor;
+  v.finished = nullptr;
+  v.n_tasks = a.n_tasks;
+  v.prefix = a.n_ready_prefix;
+  v.claim_k = a.claim_k;
+  v.seq = 0;
+  if (lane == 0) {
+    const uint32_t s = acquire_at(it);
+    hdr[s].kind = kHdrBegin;
+    hdr[s].owner = kOwnerAll;
+    bview[s] = v;
+    mbar_arrive(smem_addr(&full_bar[s]));
+  }
+  ++it;
+  __syncwarp();
+
+  const uint32_t P = v.prefix, N = v.n_tasks;
+  const uint32_t K = v.claim_k < 1u ? 1u : (v.claim_k > 32u ? 32u : v.claim_k);
+  const uint32_t lim = P < N ? P : N;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = queue_claim_n(v.q, K);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= N) break;
+    if (base + K <= lim) {
+      // every ticket of this claim is an electron that was ready at submit: one lane each
+      const bool act = lane < K;
+      b2_task t = {};
+      ElectronPlan c;
+      c.need = 0;
+      c.mode = 2;
+      if (act) {
+        t = v.tasks[base + lane];
+        c = plan_electron<kTileBytes>(a, t);
+      }
+      uint32_t incl = c.need;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, incl, o);
+        if ((int)lane >= o) incl += up;
+      }
+      const uint32_t total = __shfl_sync(kFull, incl, 31);
+      if (act) emit(t, base + lane, c, it + (incl - c.need), (deal + lane) % kWorkerWarps);
+      __syncwarp();
+      it += total;
+      deal += K;
+    } else {
+      if (lane == 0) {
+        for (uint32_t j = 0; j < K; ++j) {
+          const uint32_t ticket = base + j;
+          if (ticket >= N) break;
+          const uint32_t ti = ticket < P ? ticket : queue_take(v.q, ticket, N);
+          // a released dependent reads what other SMs just wrote with ordinary stores: order the
+          // acquire above before the copy engine's (async proxy) reads below
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          const b2_task t = v.tasks[ti];
+          const ElectronPlan c = plan_electron<kTileBytes>(a, t);
+          emit(t, ti, c, it, deal % kWorkerWarps);
+          it += c.need;
+          ++deal;
+        }
+      }
+      it = __shfl_sync(kFull, it, 0);
+      deal = __shfl_sync(kFull, deal, 0);
+    }
+  }
+  if (lane == 0) {
+    const uint32_t s = acquire_at(it);
+    hdr[s].kind = kHdrExit;
+    hdr[s].owner = kOwnerAll;
+    mbar_arrive(smem_addr(&full_bar[s]));
+  }
+}
+
 // kWarpMode (small-payload flavour): a streaming electron is consumed by ONE worker warp — stages are
 // dealt to the eight warps round-robin, per electron — instead of by all 256 worker threads.  An
 // electron of a few KiB is 64-256 vectors: spread over 256 threads it costs eight warps a barrier
@@ -193,7 +407,9 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
 
   if (threadIdx.x >= kWorkerThreads) {
     // ----------------------------------------------------------- producer warp --
-    if ((threadIdx.x & 31) == 0) {
+    if (kWarpMode && !kResident) {
+      coop_producer<kStages, kTileBytes>(a, hdr, legacy, bview, full_bar, empty_bar, stage_mem);
+    } else if ((threadIdx.x & 31) == 0) {
       uint32_t it = 0;   // stages handed out so far
       auto acquire = [&]() -> uint32_t {
         const uint32_t s = it % kStages;
