@@ -318,7 +318,11 @@ __device__ __forceinline__ void coop_producer(const WorkerArgs &a, StageHdr *hdr
   __syncwarp();
 
   const uint32_t P = v.prefix, N = v.n_tasks;
-  const uint32_t K = v.claim_k < 1u ? 1u : (v.claim_k > 32u ? 32u : v.claim_k);
+  // A claim is at most as wide as the stage ring: lanes that fill stages in parallel must each own a
+  // DISTINCT ring slot.  (mbarrier parity waits only tell "the previous phase" from "the current one":
+  // a lane two uses ahead of another on the same slot would sail through its wait.)
+  const uint32_t kmax = kStages < 32 ? (uint32_t)kStages : 32u;
+  const uint32_t K = v.claim_k < 1u ? 1u : (v.claim_k > kmax ? kmax : v.claim_k);
   const uint32_t lim = P < N ? P : N;
   for (;;) {
     uint32_t base = 0;
@@ -343,8 +347,18 @@ __device__ __forceinline__ void coop_producer(const WorkerArgs &a, StageHdr *hdr
         if ((int)lane >= o) incl += up;
       }
       const uint32_t total = __shfl_sync(kFull, incl, 31);
-      if (act) emit(t, base + lane, c, it + (incl - c.need), (deal + lane) % kWorkerWarps);
-      __syncwarp();
+      if (total <= (uint32_t)kStages) {
+        // the whole claim fits the ring once: every lane fills its own slots, all at the same time
+        if (act) emit(t, base + lane, c, it + (incl - c.need), (deal + lane) % kWorkerWarps);
+        __syncwarp();
+      } else {
+        // multi-tile electrons in the claim: the lanes take turns, in ticket order (planning — the
+        // part with the memory latency in it — has still been done by all of them at once)
+        for (uint32_t l = 0; l < K; ++l) {
+          if (lane == l) emit(t, base + lane, c, it + (incl - c.need), (deal + lane) % kWorkerWarps);
+          __syncwarp();
+        }
+      }
       it += total;
       deal += K;
     } else {

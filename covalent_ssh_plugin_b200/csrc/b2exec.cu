@@ -1089,7 +1089,7 @@ static int launch_worker(Device *D, b2_task *d_tasks, const uint32_t *d_succ, ui
   const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
   uint32_t k = 1;
   if (operand_bytes) k = avg <= 2048 ? 8u : avg <= 8192 ? 4u : avg <= 32768 ? 2u : 1u;
-  if (small) k = avg <= 2048 ? 32u : 16u;   // the small flavour's producer warp plans one electron per lane
+  if (small) k = 8u;   // the small flavour's producer warp plans one electron per lane (claim <= its 12-slot ring)
   while (k > 1 && (uint64_t)grid * k * 4 > n) k >>= 1;   // keep >= 4 claims per CTA: the tail stays short
   if (D->claim_k_override > 0) k = (uint32_t)D->claim_k_override;
   a.claim_k = k;
