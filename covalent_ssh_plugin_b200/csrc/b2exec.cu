@@ -88,6 +88,10 @@ struct Staging {
   cudaEvent_t ev = nullptr;   // last consumer of this slot has finished
   cudaEvent_t up = nullptr;   // upload of this slot has finished (task tables)
   bool in_flight = false;
+  // slot last used by a batch of the resident worker that queued nothing else: reusable once the worker's
+  // `done` word (mirrored in mapped host memory) has passed this sequence number — no event involved
+  volatile const uint32_t *res_done = nullptr;
+  uint32_t res_seq = 0;
 };
 
 struct Device {
@@ -148,6 +152,8 @@ struct Device {
   int res_ctas_per_sm = 0;         // every CTA of an instance must be co-resident (they wait for each other)
   uint64_t res_batches = 0, res_launches = 0;
   bool compute_dirty = false;      // real work sits on the compute stream that a later batch may depend on
+  uint32_t res_unwaited = 0;       // != 0: the compute stream has not been ordered after resident batch (this - 1) yet
+  uint32_t res_last_pure = 0;      // set by resident_publish for launch_locked: seq + 1 of the batch just published
   struct Table {                 // resident task table (b2_table_create)
     uint8_t *d_pristine = nullptr;   // [n tasks][n_succ successor indices] as uploaded
     uint8_t *d_work = nullptr;       // working copy of the tasks (dependency counters are consumed)
@@ -173,6 +179,7 @@ struct Device {
   uint8_t ticket_phase[kTickets] = {};
   int8_t ticket_slot[kTickets] = {};       // task-ring slot holding the batch's table (-1: none)
   uint32_t ticket_ntasks[kTickets] = {};
+  uint32_t ticket_res_seq[kTickets] = {};  // != 0: no event — complete when the resident worker's done word reaches this
   std::condition_variable ticket_cv;       // signalled when an async ticket gets recorded
   cudaEvent_t user_ev[kMaxUserEvents] = {};
   uint32_t n_user_ev = 0;
@@ -191,6 +198,7 @@ struct Device {
 Device g_dev[kMaxDevices];
 
 int resident_quiesce(Device *D);
+int compute_after_resident(Device *D);
 
 Device *get(int dev) {
   if (dev < 0 || dev >= kMaxDevices) return nullptr;
@@ -219,7 +227,23 @@ void drain_submissions(Device *D) {
   if (!D->up) return fail(B2_E_STATE, "device %d is not initialised (call b2_init)", dev); \
   CU(cudaSetDevice(dev))
 
+// ... and, for calls that queue work on the compute stream, after every batch published to the
+// resident worker (see compute_after_resident).
+#define DEV_ORDERED_SYNCED(D, dev) \
+  DEV_ORDERED(D, dev);              \
+  {                                 \
+    int rc_res_ = compute_after_resident(D); \
+    if (rc_res_) return rc_res_;    \
+  }
+
 int staging_reserve(Staging &s, size_t bytes) {
+  if (s.res_done) {
+    for (int spins = 0; (int32_t)(*s.res_done - s.res_seq) < 0; ++spins) {
+      if (spins > 50000000) return fail(B2_E_CUDA, "resident worker never completed the batch that holds this slot");
+      if (spins > 256) std::this_thread::yield();
+    }
+    s.res_done = nullptr;
+  }
   if (s.in_flight) {
     CU(cudaEventSynchronize(s.ev));
     s.in_flight = false;
@@ -353,6 +377,10 @@ int move_spans_locked(Device *D, const b2_span *spans, uint32_t n, uint32_t src_
 // Everything issued on the compute stream so far happens before whatever is queued on the
 // egress stream next.
 int egress_after_compute(Device *D) {
+  {
+    int rc_ = compute_after_resident(D);
+    if (rc_) return rc_;
+  }
   CU(cudaEventRecord(D->to_egress, D->stream));
   CU(cudaStreamWaitEvent(D->egress, D->to_egress, 0));
   return B2_OK;
@@ -478,12 +506,22 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
     D->compute_dirty = false;
   }
   CUD(g_write32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->doorbell, seq + 1, CU_STREAM_WRITE_VALUE_DEFAULT));
-  // everything queued on the compute stream after this point is ordered after the batch: the
-  // existing egress / ticket logic (events recorded on the compute stream) needs no other change
-  CUD(g_wait32(D->stream, (CUdeviceptr)(uintptr_t)&D->d_ctl->done, seq + 1, CU_STREAM_WAIT_VALUE_GEQ));
+  // The compute stream is ordered after this batch LAZILY (compute_after_resident): only when something
+  // is about to be queued behind it — a status / result download, a span move, a ticket event.  A pure
+  // stream of launches costs two stream operations per batch: the table upload and the doorbell.
+  D->res_unwaited = seq + 1;
+  D->res_last_pure = seq + 1;
   D->res_submitted = seq + 1;
   D->res_batches += 1;
   D->stats.electrons += n;
+  return B2_OK;
+}
+
+// Orders the compute stream after every batch published to the resident worker so far.
+int compute_after_resident(Device *D) {
+  if (!D->res_unwaited) return B2_OK;
+  CUD(g_wait32(D->stream, (CUdeviceptr)(uintptr_t)&D->d_ctl->done, D->res_unwaited, CU_STREAM_WAIT_VALUE_GEQ));
+  D->res_unwaited = 0;
   return B2_OK;
 }
 
@@ -495,6 +533,7 @@ int resident_quiesce(Device *D) {
   CU(cudaStreamSynchronize(D->res_stream));
   D->h_res->stop = 0;
   D->res_live = false;
+  D->res_unwaited = 0;             // everything published has completed
   return B2_OK;
 }
 
@@ -827,7 +866,7 @@ int b2_detach_host_buffer(int dev, int which) {
 }
 
 int b2_h2d(int dev, uint64_t host_off, uint64_t dev_off, uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (host_off + bytes > D->h_in_bytes || host_off + bytes < host_off)
     return fail(B2_E_ARG, "h2d: host range [%llu, +%llu) outside ingress staging (%llu bytes)",
                 (unsigned long long)host_off, (unsigned long long)bytes,
@@ -861,7 +900,7 @@ int b2_d2h(int dev, uint64_t dev_off, uint64_t host_off, uint64_t bytes) {
 }
 
 int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (!src && bytes) return fail(B2_E_ARG, "src is NULL");
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "write: device range outside arena");
@@ -872,7 +911,7 @@ int b2_write(int dev, uint64_t dev_off, const void *src, uint64_t bytes) {
 }
 
 int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (!dst && bytes) return fail(B2_E_ARG, "dst is NULL");
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "read: device range outside arena");
@@ -883,7 +922,7 @@ int b2_read(int dev, uint64_t dev_off, void *dst, uint64_t bytes) {
 }
 
 int b2_fill(int dev, uint64_t dev_off, int byte_value, uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (dev_off + bytes > D->arena_bytes[0] || dev_off + bytes < dev_off)
     return fail(B2_E_ARG, "fill: device range outside arena");
   if (!bytes) return B2_OK;
@@ -937,7 +976,7 @@ int b2_unpack(int dev, uint64_t src_off, const uint64_t *dst_offs, const uint64_
 // -------------------------------------------------- callback table + queue --
 int b2_register(int dev, uint32_t fn_id, int kind, double alpha, double beta, int64_t ialpha,
                 int64_t ibeta) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (fn_id >= B2_MAX_FN) return fail(B2_E_ARG, "fn_id %u >= B2_MAX_FN", fn_id);
   if (kind < 0 || kind >= B2_K__COUNT) return fail(B2_E_ARG, "unknown callback kind %d", kind);
   if (fn_id == 0 && kind != B2_K_NONE)
@@ -1033,12 +1072,26 @@ static uint64_t alloc_ticket(Device *D, TicketPhase phase) {
   D->ticket_phase[i] = phase;
   D->ticket_slot[i] = -1;
   D->ticket_ntasks[i] = 0;
+  D->ticket_res_seq[i] = 0;
   return t;
+}
+
+// Ticket of a batch that went to the resident worker and queued nothing else (no status copy, no
+// download): it is complete when the worker's `done` word — mirrored into mapped host memory — has
+// reached the batch's sequence number.  No CUDA event is recorded for it.
+static void resident_ticket(Device *D, uint64_t t, uint32_t seq_plus_one) {
+  const int i = (int)(t % kTickets);
+  D->ticket_res_seq[i] = seq_plus_one;
+  D->ticket_recorded[i] = true;
 }
 
 // Records ticket t's event after everything issued so far (compute stream and, if copies are
 // queued there, the egress stream).
 static int record_ticket_event(Device *D, uint64_t t) {
+  {
+    int rc_ = compute_after_resident(D);
+    if (rc_) return rc_;
+  }
   const int i = (int)(t % kTickets);
   cudaEvent_t &ev = D->tickets[i];
   if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1130,6 +1183,7 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   }
 
   uint32_t *slot_status = reinterpret_cast<uint32_t *>(s.d + succ_off + (size_t)D->succ_cap * 4);
+  D->res_last_pure = 0;
   {
     int rc_ = launch_worker(D, reinterpret_cast<b2_task *>(s.d), reinterpret_cast<const uint32_t *>(s.d + succ_off),
                             slot_status, n, D->pend_prefix, D->pend_bytes);
@@ -1138,14 +1192,24 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
   CU(cudaGetLastError());
   // the slot (pinned table + device mirror + status words) is reusable once this kernel — and the
   // status copy below, if any — is done
-  if (status_host_off == UINT64_MAX) CU(cudaEventRecord(s.ev, D->stream));
-  s.in_flight = true;
-  if (status_host_off != UINT64_MAX) {
-    int rc_ = egress_after_compute(D);
+  if (status_host_off == UINT64_MAX) {
+    if (D->res_last_pure) {
+      // resident batch with nothing else queued behind it: the slot is held by the batch's sequence
+      // number (the worker's done word in mapped host memory), no event
+      s.res_done = &D->h_res->done;
+      s.res_seq = D->res_last_pure;
+    } else {
+      CU(cudaEventRecord(s.ev, D->stream));
+      s.in_flight = true;
+    }
+  } else {
+    D->res_last_pure = 0;                   // a download follows: the ticket is an event on the egress stream
+    int rc_ = egress_after_compute(D);      // (also orders the compute stream after the resident batch)
     if (rc_) return rc_;
     CU(cudaMemcpyAsync(D->h_out + status_host_off, slot_status, (size_t)n * 4, cudaMemcpyDeviceToHost,
                        D->egress));
     CU(cudaEventRecord(s.ev, D->egress));
+    s.in_flight = true;
     D->egress_dirty = true;
     D->stats.bytes_d2h += (uint64_t)n * 4;
   }
@@ -1169,8 +1233,12 @@ int b2_launch(int dev, uint64_t status_host_off, uint64_t *ticket) {
   Range r_("b2_launch");
   DEV_ORDERED(D, dev);
   const uint64_t t = alloc_ticket(D, kPhaseNone);
+  D->res_last_pure = 0;
   int rc = launch_locked(D, status_host_off, t);
-  if (rc == B2_OK) rc = record_ticket_event(D, t);
+  if (rc == B2_OK) {
+    if (D->res_last_pure) resident_ticket(D, t, D->res_last_pure);
+    else rc = record_ticket_event(D, t);
+  }
   if (rc) {
     // the ticket exists but will never complete normally: make poll / wait report the failure
     const int i = (int)(t % kTickets);
@@ -1199,7 +1267,7 @@ int b2_table_create(int dev, const b2_task *tasks, uint32_t n, const uint32_t *s
   if (!table_id) return fail(B2_E_ARG, "table_id is NULL");
   if (!n || !tasks) return fail(B2_E_ARG, "empty table");
   if (n_succ && !succ) return fail(B2_E_ARG, "succ is NULL but n_succ = %u", n_succ);
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (n > D->qcap) return fail(B2_E_NOMEM, "table of %u electrons exceeds queue capacity %u", n, D->qcap);
   uint32_t id = 0;
   for (; id < D->tables.size(); ++id)
@@ -1260,12 +1328,24 @@ int b2_table_launch(int dev, uint32_t table_id, uint64_t status_host_off, uint64
   const size_t tab_bytes = (size_t)tb.n * sizeof(b2_task);
   b2_task *d_tasks = reinterpret_cast<b2_task *>(tb.d_pristine);
   if (tb.has_deps) {   // the worker counts the dependency words down: every launch starts from the pristine copy
+    {   // the previous launch of this table must be done with the working copy before it is re-armed
+      int rc_ = compute_after_resident(D);
+      if (rc_) return rc_;
+    }
     CU(cudaMemcpyAsync(tb.d_work, tb.d_pristine, tab_bytes, cudaMemcpyDeviceToDevice, D->stream));
+    D->compute_dirty = true;
     d_tasks = reinterpret_cast<b2_task *>(tb.d_work);
   }
+  D->res_last_pure = 0;
   int rc = launch_worker(D, d_tasks, reinterpret_cast<const uint32_t *>(tb.d_pristine + tab_bytes), tb.d_status,
                          tb.n, tb.prefix, tb.bytes);
   if (rc) return rc;
+  if (status_host_off == UINT64_MAX && D->res_last_pure) {   // resident batch, nothing else queued: no event
+    const uint64_t t = alloc_ticket(D, kPhaseNone);
+    resident_ticket(D, t, D->res_last_pure);
+    if (ticket) *ticket = t;
+    return B2_OK;
+  }
   if (status_host_off != UINT64_MAX) {
     rc = egress_after_compute(D);
     if (rc) return rc;
@@ -1278,7 +1358,7 @@ int b2_table_launch(int dev, uint32_t table_id, uint64_t status_host_off, uint64
 }
 
 int b2_table_destroy(int dev, uint32_t table_id) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (table_id >= D->tables.size() || !D->tables[table_id].live)
     return fail(B2_E_ARG, "unknown table %u", table_id);
   CU(cudaStreamSynchronize(D->stream));
@@ -1349,6 +1429,11 @@ static int ticket_lookup(Device *D, uint64_t ticket, cudaEvent_t *ev) {
   const int i = (int)(ticket % kTickets);
   if (!D->ticket_recorded[i]) return B2_E_NOTREADY;
   if (D->ticket_err[i]) return fail(D->ticket_err[i], "%s", D->ticket_msg[i].c_str());
+  if (D->ticket_res_seq[i]) {          // resident batch: no event, a sequence number
+    if (!D->h_res || (int32_t)(D->h_res->done - D->ticket_res_seq[i]) >= 0) return 1;
+    *ev = nullptr;
+    return 2;
+  }
   *ev = D->tickets[i];
   return B2_OK;
 }
@@ -1358,6 +1443,7 @@ int b2_poll(int dev, uint64_t ticket) {
   cudaEvent_t ev = nullptr;
   const int rc = ticket_lookup(D, ticket, &ev);
   if (rc == 1) return B2_OK;
+  if (rc == 2) return B2_E_NOTREADY;
   if (rc != B2_OK) return rc;
   cudaError_t e = cudaEventQuery(ev);
   if (e == cudaSuccess) return B2_OK;
@@ -1380,6 +1466,19 @@ int b2_wait(int dev, uint64_t ticket) {
       if (!D->up) return fail(B2_E_STATE, "device %d was shut down while waiting", dev);
     }
     if (rc == 1) return B2_OK;
+    if (rc == 2) {
+      // a resident batch: wait for the worker's done word (mapped host memory) outside the lock
+      const volatile uint32_t *done = &D->h_res->done;
+      const volatile uint32_t *err = &D->h_res->error;
+      const uint32_t want = D->ticket_res_seq[ticket % kTickets];
+      lk.unlock();
+      for (uint64_t spins = 0; (int32_t)(*done - want) < 0; ++spins) {
+        if (*err) return fail(B2_E_CUDA, "resident worker left with a submitted batch pending (lifetime cap)");
+        if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        else if (spins > 200) std::this_thread::yield();
+      }
+      return B2_OK;
+    }
     if (rc != B2_OK) return rc;
     CU(cudaSetDevice(dev));
   }
@@ -1401,7 +1500,7 @@ int b2_wait(int dev, uint64_t ticket) {
 int b2_sync(int dev) {
   cudaStream_t st, up, eg;
   {
-    DEV_ORDERED(D, dev);
+    DEV_ORDERED_SYNCED(D, dev);
     st = D->stream;
     up = D->upload;
     eg = D->egress;
@@ -1709,7 +1808,7 @@ int b2_ipc_open(int dev, const void *handle64, uint64_t peer_arena_bytes, uint32
 
 int b2_peer_copy(int dev, uint32_t dst_arena_id, uint64_t src_off, uint64_t dst_off,
                  uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (dst_arena_id >= (uint32_t)D->n_arenas) return fail(B2_E_ARG, "unknown arena id %u", dst_arena_id);
   if (src_off + bytes > D->arena_bytes[0] || dst_off + bytes > D->arena_bytes[dst_arena_id])
     return fail(B2_E_ARG, "peer_copy: range outside arena");
@@ -1737,7 +1836,7 @@ int b2_event_create(int dev, uint32_t *event_id) {
 }
 
 int b2_event_record(int dev, uint32_t event_id) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (event_id >= D->n_user_ev) return fail(B2_E_ARG, "unknown event %u", event_id);
   CU(cudaEventRecord(D->user_ev[event_id], D->stream));
   return B2_OK;
@@ -1759,7 +1858,7 @@ int b2_event_elapsed_ms(int dev, uint32_t start_id, uint32_t stop_id, float *ms)
 }
 
 int b2_flush_l2(int dev, uint64_t scratch_off, uint64_t bytes) {
-  DEV_ORDERED(D, dev);
+  DEV_ORDERED_SYNCED(D, dev);
   if (scratch_off + bytes > D->arena_bytes[0]) return fail(B2_E_ARG, "flush range outside arena");
   static int v = 0;
   CU(cudaMemsetAsync(D->arena[0] + scratch_off, (++v) & 0xff, bytes, D->stream));
