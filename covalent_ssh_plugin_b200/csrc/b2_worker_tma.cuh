@@ -103,18 +103,9 @@ struct ResidentBatch {     // one ring entry: written by the host into mapped pi
   b2_task *tasks;
   const uint32_t *succ;
   uint32_t *status;
-  uint32_t n_tasks, prefix, claim_k;
-  uint32_t flags;          // kResCpuDoorbell: runnable as soon as seq_tag says so (see below)
-  uint32_t seq_tag;        // written LAST by the host: batch sequence number + 1
-  uint32_t pad;
-  uint64_t pad2[2];
+  uint32_t n_tasks, prefix, claim_k, pad;
+  uint64_t pad2[3];
 };
-// A batch whose table needs no upload (every electron ready at submit: the worker only READS the table,
-// so it can read it straight out of mapped pinned host memory) and whose operands are already resident
-// is published with plain CPU stores — table, ring entry, then the entry's seq_tag — and no CUDA call at
-// all: the mapped-memory doorbell.  Batches with anything stream-ordered in front of them (payload
-// upload, table upload) ring the device-memory doorbell through the upload stream instead.
-constexpr uint32_t kResCpuDoorbell = 1u;
 struct ResidentQ {         // per-batch queue counters (zero when the slot is handed to a batch)
   uint32_t head, tail, cursor, finished;
   uint32_t pad[12];
@@ -630,20 +621,14 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
             ra.host->state = (ra.instance << 2) | 1u;
             for (;;) {
               const uint32_t published = ld_acquire_sys_u32(&ctl->doorbell);
-              const volatile ResidentBatch *he = &ra.host->ring[b % kResRing];
-              bool ready = (int32_t)(published - b) > 0;       // stream-ordered doorbell (device memory)
-              if (!ready && he->seq_tag == b + 1u && (he->flags & kResCpuDoorbell)) {
-                __threadfence_system();                         // tag before body
-                ready = true;                                   // mapped-memory doorbell (host memory, over PCIe)
-              }
-              if (ready) {
+              if ((int32_t)(published - b) > 0) {
                 // at most two batches are in flight (two sets of queue cells): b starts once b-2 is done
                 const uint32_t dn = ld_acquire_gpu_u32(&ctl->done);
                 if ((int32_t)(b - dn) <= 1) {
                   // The descriptor sits in mapped host memory (the host wrote it with ordinary stores
-                  // before it rang either doorbell): one 64-byte read over PCIe by the leader, mirrored
+                  // before it rang the doorbell): one 64-byte read over PCIe by the leader, mirrored
                   // into device memory for everybody else.
-                  const volatile uint64_t *src = reinterpret_cast<const volatile uint64_t *>(he);
+                  const volatile uint64_t *src = reinterpret_cast<const volatile uint64_t *>(&ra.host->ring[b % kResRing]);
                   uint64_t *dst = reinterpret_cast<uint64_t *>(&ctl->ring[b % kResRing]);
 #pragma unroll
                   for (int w = 0; w < (int)(sizeof(ResidentBatch) / 8); ++w) dst[w] = src[w];

@@ -83,7 +83,6 @@ enum TicketPhase : uint8_t { kPhaseNone = 0, kPhaseQueued = 1, kPhaseTabled = 2,
 // rewritten while an earlier async copy may still be reading it.
 struct Staging {
   uint8_t *h = nullptr;
-  uint8_t *h_dev = nullptr;   // device address of the (mapped) pinned buffer h
   uint8_t *d = nullptr;
   size_t cap = 0;
   cudaEvent_t ev = nullptr;   // last consumer of this slot has finished
@@ -256,11 +255,9 @@ int staging_reserve(Staging &s, size_t bytes) {
     if (s.h) cudaFreeHost(s.h);
     if (s.d) cudaFree(s.d);
     s.h = nullptr;
-    s.h_dev = nullptr;
     s.d = nullptr;
     s.cap = 0;
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&s.h), ncap, cudaHostAllocMapped));
-    CU(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_dev), s.h, 0));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&s.h), ncap, cudaHostAllocDefault));
     CU(cudaMalloc(reinterpret_cast<void **>(&s.d), ncap));
     s.cap = ncap;
   }
@@ -470,7 +467,7 @@ int resident_launch_instance(Device *D) {
 
 // Publishes one batch to the resident worker instead of launching a kernel for it.
 int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32_t *d_status, uint32_t n,
-                     uint32_t prefix, uint64_t operand_bytes, bool cpu_doorbell) {
+                     uint32_t prefix, uint64_t operand_bytes) {
   const uint32_t seq = D->res_submitted;
   const uint32_t slot = seq % kResRing;
   // the ring entry being replaced belongs to batch seq - kResRing: wait (on the host) until it is done.
@@ -493,11 +490,7 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
   rb.n_tasks = n;
   rb.prefix = prefix;
   rb.claim_k = k;
-  rb.flags = cpu_doorbell ? kResCpuDoorbell : 0u;
-  rb.seq_tag = 0;                                            // the tag goes last, below
-  D->h_res->ring[slot].seq_tag = 0;
-  __sync_synchronize();
-  memcpy(const_cast<ResidentBatch *>(&D->h_res->ring[slot]), &rb, sizeof rb);   // plain stores; visible before either doorbell
+  memcpy(const_cast<ResidentBatch *>(&D->h_res->ring[slot]), &rb, sizeof rb);   // plain stores; visible before the doorbell
   // exit handshake, host half: announce the batch BEFORE any of its stream operations, then look
   // at the kernel's state.  If the instance we launched last is leaving, queue another one behind it.
   D->h_res->submitted = seq + 1;
@@ -507,21 +500,12 @@ int resident_publish(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32
     int rc = resident_launch_instance(D);
     if (rc) return rc;
   }
-  if (cpu_doorbell) {
-    // mapped-memory doorbell: nothing stream-ordered precedes this batch (operands resident, table read
-    // in place from mapped pinned memory) — the tag store publishes it, no CUDA call is made
-    __sync_synchronize();
-    D->h_res->ring[slot].seq_tag = seq + 1;
-    __sync_synchronize();
-  } else {
-    if (D->compute_dirty) {   // e.g. a b2_h2d this batch reads from: the doorbell must not overtake it
-      CU(cudaEventRecord(D->to_egress, D->stream));
-      CU(cudaStreamWaitEvent(D->upload, D->to_egress, 0));
-      D->compute_dirty = false;
-    }
-    D->h_res->ring[slot].seq_tag = seq + 1;
-    CUD(g_write32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->doorbell, seq + 1, CU_STREAM_WRITE_VALUE_DEFAULT));
+  if (D->compute_dirty) {   // e.g. a b2_h2d this batch reads from: the doorbell must not overtake it
+    CU(cudaEventRecord(D->to_egress, D->stream));
+    CU(cudaStreamWaitEvent(D->upload, D->to_egress, 0));
+    D->compute_dirty = false;
   }
+  CUD(g_write32(D->upload, (CUdeviceptr)(uintptr_t)&D->d_ctl->doorbell, seq + 1, CU_STREAM_WRITE_VALUE_DEFAULT));
   // The compute stream is ordered after this batch LAZILY (compute_after_resident): only when something
   // is about to be queued behind it — a status / result download, a span move, a ticket event.  A pure
   // stream of launches costs two stream operations per batch: the table upload and the doorbell.
@@ -1136,9 +1120,8 @@ static int record_ticket(Device *D, uint64_t *ticket) {
 // device.  Picks the streaming flavour from the average operand size: electrons of a few KiB run
 // on the 12 x 4 KiB-stage kernel and claim several tickets per fetch-add.
 static int launch_worker(Device *D, b2_task *d_tasks, const uint32_t *d_succ, uint32_t *d_status,
-                         uint32_t n, uint32_t prefix, uint64_t operand_bytes, bool cpu_doorbell = false) {
-  if (D->res_enabled && D->worker_tma)
-    return resident_publish(D, d_tasks, d_succ, d_status, n, prefix, operand_bytes, cpu_doorbell);
+                         uint32_t n, uint32_t prefix, uint64_t operand_bytes) {
+  if (D->res_enabled && D->worker_tma) return resident_publish(D, d_tasks, d_succ, d_status, n, prefix, operand_bytes);
   WorkerArgs a;
   fill_worker_consts(D, a);
   a.tasks = d_tasks;
@@ -1187,32 +1170,24 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
                 (unsigned long long)status_host_off, n);
   Staging &s = D->task_ring[D->task_slot];
   const size_t succ_off = (size_t)D->qcap * sizeof(b2_task);
-  // Resident worker, plain fan-out (every electron ready at submit, so the worker only reads the table),
-  // nothing stream-ordered pending in front of it: the worker reads the table in place from the mapped
-  // pinned slot and the batch is published with CPU stores alone.
-  const bool in_place = D->res_enabled && D->worker_tma && D->pend_succ == 0 && D->pend_prefix == n &&
-                        !D->compute_dirty && s.h_dev != nullptr;
+  // The table travels on its own stream: the upload for this launch overlaps
+  // whatever the compute stream is still running; the kernel waits for it.
+  if (!s.up) CU(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
+  CU(cudaMemcpyAsync(s.d, s.h, (size_t)n * sizeof(b2_task), cudaMemcpyHostToDevice, D->upload));
+  if (D->pend_succ)
+    CU(cudaMemcpyAsync(s.d + succ_off, s.h + succ_off, (size_t)D->pend_succ * 4,
+                       cudaMemcpyHostToDevice, D->upload));
+  if (!(D->res_enabled && D->worker_tma)) {   // resident worker: the doorbell follows the table on the upload stream
+    CU(cudaEventRecord(s.up, D->upload));
+    CU(cudaStreamWaitEvent(D->stream, s.up, 0));
+  }
+
   uint32_t *slot_status = reinterpret_cast<uint32_t *>(s.d + succ_off + (size_t)D->succ_cap * 4);
   D->res_last_pure = 0;
-  if (in_place) {
-    int rc_ = launch_worker(D, reinterpret_cast<b2_task *>(s.h_dev), nullptr, slot_status, n, n, D->pend_bytes, true);
-    if (rc_) return rc_;
-  } else {
-    // The table travels on its own stream: the upload for this launch overlaps
-    // whatever the compute stream is still running; the kernel waits for it.
-    if (!s.up) CU(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
-    CU(cudaMemcpyAsync(s.d, s.h, (size_t)n * sizeof(b2_task), cudaMemcpyHostToDevice, D->upload));
-    if (D->pend_succ)
-      CU(cudaMemcpyAsync(s.d + succ_off, s.h + succ_off, (size_t)D->pend_succ * 4,
-                         cudaMemcpyHostToDevice, D->upload));
-    if (!(D->res_enabled && D->worker_tma)) {   // resident worker: the doorbell follows the table on the upload stream
-      CU(cudaEventRecord(s.up, D->upload));
-      CU(cudaStreamWaitEvent(D->stream, s.up, 0));
-    }
+  {
     int rc_ = launch_worker(D, reinterpret_cast<b2_task *>(s.d), reinterpret_cast<const uint32_t *>(s.d + succ_off),
                             slot_status, n, D->pend_prefix, D->pend_bytes);
     if (rc_) return rc_;
-    D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
   }
   CU(cudaGetLastError());
   // the slot (pinned table + device mirror + status words) is reusable once this kernel — and the
@@ -1238,6 +1213,7 @@ static int launch_locked(Device *D, uint64_t status_host_off, uint64_t t) {
     D->egress_dirty = true;
     D->stats.bytes_d2h += (uint64_t)n * 4;
   }
+  D->stats.bytes_h2d += (uint64_t)n * sizeof(b2_task) + (uint64_t)D->pend_succ * 4;
   if (t) {
     const int ti = (int)(t % kTickets);
     D->ticket_slot[ti] = (int8_t)D->task_slot;
