@@ -78,6 +78,33 @@ def test_back_to_back_batches_without_launches(res_device):
         assert np.array_equal(got[o:o + elems], np.float32(2.0) * src[o:o + elems] + np.float32(1.0)), i
 
 
+def test_reused_table_slots_never_go_stale(res_device):
+    """The eight task-table slots are reused cyclically and — for batches that queue nothing else — are
+    guarded by the batch's sequence number instead of an event.  Every batch here carries different
+    records at addresses an earlier batch also used: a slot handed out too early, or a stale cached
+    line, would show up as a wrong sum."""
+    L, dev = res_device["L"], res_device["dev"]
+    n, reps = 777, 48
+    base = 2 * GiB
+    t = C.c_uint64()
+    tickets = []
+    for rep in range(reps):
+        tasks = np.zeros(n, dtype=L.TASK_DTYPE)
+        tasks["fn_id"], tasks["flags"], tasks["count"] = 23, L.F_IMM0 | L.F_IMM1, 1
+        tasks["arg0"], tasks["arg1"] = np.arange(n) * 3 + rep, 1000 * rep
+        tasks["out"] = base + 8 * (rep * n + np.arange(n))
+        L.call("b2_enqueue", dev, tasks.ctypes.data, n, None, 0, None)
+        L.call("b2_launch", dev, L.NO_STATUS_COPY, C.byref(t))
+        tickets.append(t.value)
+    for tk in tickets[::7] + [tickets[-1]]:
+        L.call("b2_wait", dev, tk)
+    assert L.load().b2_poll(dev, tickets[0]) == 0
+    got = np.empty(reps * n, dtype=np.int64)
+    L.call("b2_read", dev, base, got.ctypes.data, got.nbytes)
+    want = np.concatenate([np.arange(n) * 3 + rep + 1000 * rep for rep in range(reps)])
+    assert np.array_equal(got, want)
+
+
 def test_dependencies_inside_a_resident_batch(res_device):
     """A 300-long chain of integer adds plus a fan-out/fan-in diamond, released on the device through
     the batch's own queue cells — in resident mode those are per-batch state in the control block."""
