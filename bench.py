@@ -891,6 +891,8 @@ def sweep_c5(L, eng, ex, electrons, spec, timed, peak, dev, heap0, heap_used):
             row["e2e_exact"] = bool(np.array_equal(out[-1], np.float32(2.0) * xs[(n_e2e - 1) % len(xs)] + np.float32(1.0)))
             del out
             row.update(e2e_electrons=n_e2e, e2e_electrons_per_s=n_e2e / dt, e2e_gbs_in_plus_out=2.0 * n_e2e * P / dt / 1e9)
+        else:
+            row["e2e_skipped"] = "operand larger than half a staging segment of this bench's engine (sized for 256 x 64 KiB batches)"
         rows.append(row)
     return {"workload": "C5: payload sweep, one GPU, scale_add electrons; worker on device-resident operands "
                         f"({budget // MiB} MiB of payloads per cell, at most 100 000 electrons; electrons >= 2 MiB go out as "
