@@ -730,7 +730,7 @@ __device__ __forceinline__ void worker_tma_body(const WorkerArgs &a, const Resid
         if (lane == 0) mbar_arrive(smem_addr(&empty_bar[s]));
         continue;
       }
-      if (kind == kHdrEnd) {
+      if (kResident && kind == kHdrEnd) {
         // resident: this CTA has retired its share of the batch.  The last CTA to say so completes
         // the batch: re-arms the slot's counters and publishes `done` for the egress stream.
         worker_sync();                                  // every store of this CTA for the batch is issued

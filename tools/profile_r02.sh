@@ -15,13 +15,17 @@ echo "== compute-sanitizer --tool memcheck (submit / cancel / tables / both work
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 99 --target-processes all \
   python -m pytest tests/test_submit_gpu.py -m gpu -x -q -k "not 70000 and not 16384 and not 3145733" > gpurun_out/r02_sanitize_memcheck_submit.log 2>&1
 echo "exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/r02_sanitize_memcheck_submit.log | tail -3
+echo "== compute-sanitizer --tool memcheck (resident worker)"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 --target-processes all \
+  python -m pytest tests/test_resident_gpu.py -m gpu -x -q -p no:timeout > gpurun_out/r02_sanitize_memcheck_resident.log 2>&1
+echo "exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/r02_sanitize_memcheck_resident.log | tail -3
 echo "== compute-sanitizer --tool racecheck (B2_WORKER=classic B2_MOVER=ldg)"
 B2_WORKER=classic B2_MOVER=ldg timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 99 --target-processes all \
   python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/r02_sanitize_racecheck_classic.log 2>&1
 echo "exit $?"; grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/r02_sanitize_racecheck_classic.log | tail -3
 
 echo "== ncu launch list of the bench command"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv \
   python bench.py --steps 3 --warmup 3 --quick --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1
 echo "exit $?"
 for k in worker_tma_kernel worker_tma_small_kernel span_move_tma_kernel; do
