@@ -490,6 +490,8 @@ def run_cuda_arm(args, dist: Dist):
     # 10 000 electrons as ceil(n / max_batch) batches per step: one kernel launch each, or published to
     # the resident worker (b2_resident_enable) through its doorbell — no launch, no gap between batches.
     try:
+        if os.environ.get("B2_BENCH_SKIP_RESIDENT") == "1":     # profiler runs: ncu serialises kernels, a resident
+            raise RuntimeError("skipped (B2_BENCH_SKIP_RESIDENT=1)")   # instance would sit out its lifetime cap per batch
         per_size = {}
         for bsz in sorted({max_batch, 1024}):
             small_tabs = []

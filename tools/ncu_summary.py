@@ -28,8 +28,16 @@ def launches(path):
     for r in data:
         if len(r) > vi:
             agg.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
+    # The resident worker cannot be profiled launch by launch: ncu serialises kernels, so the stream-ordered
+    # doorbell cannot arrive while an instance is being measured and every instance runs to its lifetime cap.
+    artefact = {k: v for k, v in agg.items() if k.startswith("worker_resident_kernel")}
+    for k in artefact:
+        agg.pop(k)
     tot = sum(sum(v) for v in agg.values())
     print(f"# launch list: {path}  (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised)")
+    for k, v in artefact.items():
+        print(f"# excluded from the shares: {k} x{len(v)}, {sum(v) / len(v) / 1e3:.0f} us each = its lifetime cap (profiling artefact: "
+              "under ncu the doorbell cannot arrive while the instance is being measured)")
     for k, v in agg.items():
         print(f"{k:34s} launches={len(v):4d} total_us={sum(v) / 1e3:10.1f} avg_us={sum(v) / len(v) / 1e3:8.1f} "
               f"share={100 * sum(v) / tot:5.1f}% min_us={min(v) / 1e3:.1f} max_us={max(v) / 1e3:.1f}")

@@ -25,7 +25,7 @@ B2_WORKER=classic B2_MOVER=ldg timeout 1200 compute-sanitizer --tool racecheck -
 echo "exit $?"; grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/r02_sanitize_racecheck_classic.log | tail -3
 
 echo "== ncu launch list of the bench command"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv \
+B2_BENCH_SKIP_RESIDENT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv \
   python bench.py --steps 3 --warmup 3 --quick --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1
 echo "exit $?"
 for k in worker_tma_kernel worker_tma_small_kernel span_move_tma_kernel; do
