@@ -612,6 +612,7 @@ def run_cuda_arm(args, dist: Dist):
     h2d = (c1["bytes_in"] - c0["bytes_in"]) // e2e_steps + 64 * len(mine)
     d2h = (c1["bytes_out"] - c0["bytes_out"]) // e2e_steps + 4 * len(mine)
     e2e_launches = int((st1.launches_worker - st0.launches_worker) + (st1.launches_pack - st0.launches_pack))
+    e2e_launches = int(sum(dist.gather(float(e2e_launches))))           # kernels launched by all ranks in the timed steps
     value = n / e2e_s
     if rank == 0:
         print(f"[bench] worker_step {ms_dev_max:.4f} ms ({worker_gbs / peak:.3f} of peak; resident table {res_gbs / peak:.3f}), pack {kernels['pack']['frac']:.3f}, "
