@@ -191,6 +191,7 @@ _inflight: Dict[str, _InFlight] = {}
 # the engines: executor attributes stay plain data.
 _live: Dict[tuple, tuple] = {}
 _CANCELLED = object()                # waiter result that means "tombstoned by cancel()"
+_Future = asyncio.Future
 
 _STATUS_TEXT = {_b2lib.TS_OVERFLOW: "integer result does not fit int64",
                 _b2lib.TS_BAD_FN: "no device callback registered for this electron",
@@ -528,7 +529,7 @@ class SSHExecutor(RemoteExecutor):
                     live_key = (self.hostname, task_metadata["dispatch_id"], task_metadata["node_id"])
                     outcome = None
                     if not batch.done:
-                        fut = loop.create_future()
+                        fut = _Future(loop=loop)            # (loop.create_future() minus one Python frame)
                         batch.waiters.append(fut)
                         _live[live_key] = (batch, index, 1, fut)
                         try:
