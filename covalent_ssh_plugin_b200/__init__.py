@@ -8,8 +8,8 @@ implementation to fall back to if it is missing.
 """
 
 from .electrons import device_electron, DeviceElectron, NotDeviceEligible  # noqa: F401
-from .ssh import SSHExecutor, EXECUTOR_PLUGIN_NAME, _EXECUTOR_PLUGIN_DEFAULTS  # noqa: F401
+from .ssh import SSHExecutor, TaskCancelledError, EXECUTOR_PLUGIN_NAME, _EXECUTOR_PLUGIN_DEFAULTS  # noqa: F401
 
-__all__ = ["SSHExecutor", "device_electron", "DeviceElectron", "NotDeviceEligible",
+__all__ = ["SSHExecutor", "device_electron", "DeviceElectron", "NotDeviceEligible", "TaskCancelledError",
            "EXECUTOR_PLUGIN_NAME"]
 __version__ = "0.1.0"
