@@ -77,7 +77,8 @@ class Clocks:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", str(max(50, env_int("B2_BENCH_CLOCKS_MS", 200)))], stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -393,7 +394,7 @@ def run_cuda_arm(args, dist: Dist):
         L.call("b2_event_elapsed_ms", dev, ev[0].value, ev[1].value, C.byref(ms))
         return ms.value / reps
 
-    clocks = Clocks(dev) if rank == 0 else None      # ONE sampler per run, not one per rank
+    clocks = Clocks(dev) if rank == 0 and env_int("B2_BENCH_CLOCKS_MS", 200) > 0 else None   # ONE sampler per run
     if clocks:
         clocks.start()
 
@@ -801,7 +802,7 @@ def run_cuda_arm(args, dist: Dist):
                     "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
                     "verified": verified,
                     "ms_per_rank": {"min": 1e3 * min(e2e_ranks), "median": 1e3 * statistics.median(e2e_ranks),
-                                    "max": 1e3 * e2e_s}},
+                                    "max": 1e3 * e2e_s, "all": [round(1e3 * t, 3) for t in e2e_ranks]}},
             "gpu_launches": e2e_launches,
             "single_dispatcher": single,
             "roofline": {"bound": "hbm", "kernel": "b2::worker_tma_kernel (fused scale_add electron: 64 KiB in, 64 KiB out)",
