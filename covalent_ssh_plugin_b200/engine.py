@@ -64,6 +64,10 @@ DEFAULTS = {
     "max_batch": int(os.environ.get("B2_MAX_BATCH", 4096)),
     "queue_cap": int(os.environ.get("B2_QUEUE_CAP", 1 << 16)),
     "zero_copy": os.environ.get("B2_ZERO_COPY", "1") != "0",
+    # resident worker (b2_resident_enable): the worker kernel outlives its batches; batches are published
+    # through a doorbell instead of a launch.  Off by default: at the batch sizes run() produces it is on a
+    # par with launching (profiles/r02_notes.md), so the simpler mode stays the default.
+    "resident": os.environ.get("B2_RESIDENT", "0") == "1",
     "gc_tune": os.environ.get("B2_GC_TUNE", "1") != "0",
     # general path only: operands of at least this many bytes become copy jobs for the
     # library's copy threads (one host thread moves ~9-11 GB/s, 8-16 threads 25-40 GB/s,
@@ -265,6 +269,9 @@ class DeviceEngine:
         self.heap_bytes = self.arena_bytes - self.heap_base
 
         L.call("b2_init", ordinal, self.arena_bytes, self.staging_in, self.staging_out, self.queue_cap)
+        self.resident = bool(c.get("resident"))
+        if self.resident:
+            L.call("b2_resident_enable", ordinal, 0)
         self.info = L.DeviceInfo()
         L.call("b2_get_info", ordinal, C.byref(self.info))
         self._h_in, _ = self._host_view(0, self.staging_in)
