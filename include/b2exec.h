@@ -19,6 +19,10 @@
  *   asyncssh.scp download        ssh.py:451          b2_pack of result slots + b2_d2h
  *   rm x3                        ssh.py:313-315      arena offsets are simply reused by the host
  *   (one dispatcher per host)    README.md:52-65     b2_peer_copy / b2_peer_pack over NVLink
+ *   the whole of run(), per batch ssh.py:466-591      b2_submit  (copy pool -> H2D -> worker -> D2H -> ticket, one call)
+ *   cancel() (unsupported)       ssh.py:460-464      b2_cancel / B2_F_CANCELLED tombstones
+ *   re-upload per electron       ssh.py:360-361      b2_table_create / b2_table_launch (resident task tables)
+ *   a fresh interpreter per run  ssh.py:377-383      b2_resident_enable (the worker kernel outlives its batches)
  *
  * Conventions
  *   - every function returns 0 (B2_OK) on success or a negative b2_err code;
