@@ -49,16 +49,6 @@ constexpr uint32_t kWorkerSmemBytes = kStages * kTileBytes;
 constexpr int kSmallStages = B2_TMA_SMALL_STAGES;
 constexpr uint32_t kSmallTileBytes = B2_TMA_SMALL_TILE;
 constexpr uint32_t kWorkerSmallSmemBytes = kSmallStages * kSmallTileBytes;
-// ... and once more for electrons of 2 KiB and less: 24 x 2 KiB (24 in flight per CTA, claims of 16)
-#ifndef B2_TMA_TINY_STAGES
-#define B2_TMA_TINY_STAGES 24
-#endif
-#ifndef B2_TMA_TINY_TILE
-#define B2_TMA_TINY_TILE 2048
-#endif
-constexpr int kTinyStages = B2_TMA_TINY_STAGES;
-constexpr uint32_t kTinyTileBytes = B2_TMA_TINY_TILE;
-constexpr uint32_t kWorkerTinySmemBytes = kTinyStages * kTinyTileBytes;
 constexpr uint32_t kHdrExit = 0xFFFFFFFFu;
 constexpr uint32_t kHdrLegacy = 0xFFFFFFFEu;
 constexpr uint32_t kHdrFailed = 0xFFFFFFFDu;          // status already decided by the producer
@@ -901,11 +891,6 @@ __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
 __global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
     worker_tma_small_kernel(const __grid_constant__ WorkerArgs a) {
   worker_tma_body<kSmallStages, kSmallTileBytes, false, true>(a, ResidentArgs{});
-}
-
-__global__ void __launch_bounds__(kCtaThreads, B2_WORKER_MIN_CTAS)
-    worker_tma_tiny_kernel(const __grid_constant__ WorkerArgs a) {
-  worker_tma_body<kTinyStages, kTinyTileBytes, false, true>(a, ResidentArgs{});
 }
 
 // The resident worker: one CTA set that outlives its batches (b2_resident_enable).  `a` supplies

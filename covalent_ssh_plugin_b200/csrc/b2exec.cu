@@ -137,7 +137,6 @@ struct Device {
 
   int worker_ctas_per_sm = 0;
   int worker_small_ctas_per_sm = 0;
-  int worker_tiny_ctas_per_sm = 0;
   int worker_small_mode = -1;    // B2_WORKER_SMALL: -1 auto (by average operand size), 0 never, 1 always
   int claim_k_override = 0;      // B2_CLAIM_K
   // resident worker (b2_resident_enable): one kernel instance outlives its batches
@@ -650,11 +649,6 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
                           (int)kWorkerSmallSmemBytes));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_small_ctas_per_sm, worker_tma_small_kernel,
                                                    kCtaThreads, kWorkerSmallSmemBytes));
-  CU(cudaFuncSetAttribute(worker_tma_tiny_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CU(cudaFuncSetAttribute(worker_tma_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)kWorkerTinySmemBytes));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D->worker_tiny_ctas_per_sm, worker_tma_tiny_kernel,
-                                                   kCtaThreads, kWorkerTinySmemBytes));
   D->worker_small_mode = env_int("B2_WORKER_SMALL", -1);
   D->claim_k_override = env_int("B2_CLAIM_K", 0);
   memset(D->h_fn_kind, 0, sizeof D->h_fn_kind);
@@ -692,7 +686,6 @@ int b2_init(int dev, uint64_t arena_bytes, uint64_t staging_in_bytes, uint64_t s
   const int wcap = env_int("B2_WORKER_CTAS_PER_SM", 0);
   if (wcap > 0) D->worker_ctas_per_sm = std::min(D->worker_ctas_per_sm, wcap);
   if (wcap > 0) D->worker_small_ctas_per_sm = std::min(D->worker_small_ctas_per_sm, wcap);
-  if (wcap > 0) D->worker_tiny_ctas_per_sm = std::min(D->worker_tiny_ctas_per_sm, wcap);
   const int mcap = env_int("B2_MOVER_CTAS_PER_SM", 0);
   if (mcap > 0) D->mover_ctas_per_sm = std::min(D->mover_ctas_per_sm, mcap);
 
@@ -1145,21 +1138,19 @@ static int launch_worker(Device *D, b2_task *d_tasks, const uint32_t *d_succ, ui
   bool small = D->worker_tma && operand_bytes && avg <= 8192;
   if (D->worker_small_mode == 0) small = false;
   if (D->worker_small_mode == 1) small = D->worker_tma;
-  const bool tiny = small && avg <= 2048 && D->worker_small_mode != 2 && D->worker_tiny_ctas_per_sm > 0;   // B2_WORKER_SMALL=2: small, never tiny
-  const int per_sm = tiny ? D->worker_tiny_ctas_per_sm : small ? D->worker_small_ctas_per_sm : D->worker_ctas_per_sm;
+  const int per_sm = small ? D->worker_small_ctas_per_sm : D->worker_ctas_per_sm;
   const int cap = D->sm_count * std::max(1, per_sm);
   const int grid = (int)std::min<uint32_t>(n, (uint32_t)cap);
   uint32_t k = 1;
   if (operand_bytes) k = avg <= 2048 ? 8u : avg <= 8192 ? 4u : avg <= 32768 ? 2u : 1u;
-  // the small flavours' producer warp plans one electron per lane; a claim never exceeds the stage ring
-  if (small) k = tiny ? 16u : 8u;
+  // the small flavour's producer warp plans one electron per lane; a claim never exceeds its 12-slot ring
+  // (24 x 2 KiB stages with claims of 16 were tried for <= 2 KiB electrons: no gain at 1 KiB, 0.40 vs 0.41)
+  if (small) k = 8u;
   while (k > 1 && (uint64_t)grid * k * 4 > n) k >>= 1;   // keep >= 4 claims per CTA: the tail stays short
   if (D->claim_k_override > 0) k = (uint32_t)D->claim_k_override;
   a.claim_k = k;
   if (!D->worker_tma)
     worker_kernel<<<grid, kCtaThreads, 0, D->stream>>>(a);
-  else if (tiny)
-    worker_tma_tiny_kernel<<<grid, kCtaThreads, kWorkerTinySmemBytes, D->stream>>>(a);
   else if (small)
     worker_tma_small_kernel<<<grid, kCtaThreads, kWorkerSmallSmemBytes, D->stream>>>(a);
   else

@@ -191,10 +191,10 @@ def _model_scale_add(x):
 
 @pytest.mark.parametrize("elems,n", [(64, 60000), (256, 40000), (1024, 30000), (3000, 4000), (16384, 1500), (70000, 300)])
 def test_both_worker_flavours_are_bit_exact(raw_device, elems, n):
-    """The host picks the streaming worker's flavour from the average operand size (24 x 2 KiB stages up to
-    2 KiB, 12 x 4 KiB up to 8 KiB — both with the cooperative producer warp and one worker warp per
-    electron — 3 x 16 KiB stages above).  Same electrons, same bytes out, whichever runs — including ragged
-    sizes that straddle tile boundaries, and launches big enough for the widest claims (16 tickets)."""
+    """The host picks the streaming worker's flavour from the average operand size (12 x 4 KiB stages up to
+    8 KiB, with the cooperative producer warp and one worker warp per electron; 3 x 16 KiB stages above).
+    Same electrons, same bytes out, whichever runs — including ragged sizes that straddle tile boundaries,
+    and launches big enough for the widest claims (8 tickets)."""
     L, dev = raw_device["L"], raw_device["dev"]
     L.call("b2_register", dev, 21, L.K_SCALE_ADD, 2.0, 1.0, 0, 0)
     rng = np.random.default_rng(elems)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, fixed workload for `ncu --set full` captures (one launch of each hot kernel at the
 sizes bench.py reports): worker_tma_kernel over 10 000 x 64 KiB scale_add electrons,
-worker_tma_small_kernel over 100 000 x 4 KiB, worker_tma_tiny_kernel over 100 000 x 1 KiB, span_move_tma_kernel packing 10 000 x 64 KiB.
+worker_tma_small_kernel over 100 000 x 4 KiB, span_move_tma_kernel packing 10 000 x 64 KiB.
 
     ncu --set full --clock-control none --import-source on -k regex:worker_tma_kernel -s 2 -c 1 \
         -o gpurun_out/prof_worker python tools/ncu_target.py
@@ -33,7 +33,7 @@ L.call("b2_move_spans", dev, spans.ctypes.data, len(spans))
 L.call("b2_sync", dev)
 t = C.c_uint64()
 reps = int(os.environ.get("B2_NCU_REPS", 4))
-for payload, n in ((65536, 10000), (4096, 100000), (1024, 100000)):
+for payload, n in ((65536, 10000), (4096, 100000)):
     tab = np.zeros(n, dtype=L.TASK_DTYPE)
     tab["fn_id"], tab["count"] = 1, payload // 4
     tab["arg0"] = src0 + np.arange(n, dtype=np.uint64) * payload

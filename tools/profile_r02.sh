@@ -28,7 +28,7 @@ echo "== ncu launch list of the bench command"
 B2_BENCH_SKIP_RESIDENT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv \
   python bench.py --steps 3 --warmup 3 --quick --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1
 echo "exit $?"
-for k in worker_tma_kernel worker_tma_small_kernel worker_tma_tiny_kernel span_move_tma_kernel; do
+for k in worker_tma_kernel worker_tma_small_kernel span_move_tma_kernel; do
   echo "== ncu --set full $k"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$k" -s 2 -c 1 -f \
     -o gpurun_out/r02_prof_$k python tools/ncu_target.py > gpurun_out/r02_ncu_$k.log 2>&1
