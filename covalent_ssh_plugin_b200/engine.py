@@ -36,12 +36,25 @@ import numpy as np
 from . import _b2lib as L
 from .electrons import DeviceElectron, DeviceRef, EncodedTask, decode, registry_size, registry_snapshot
 
-try:
-    from . import _b2host          # compiled staging helper (hostext/b2host.c)
-except ImportError as _err:        # never a silent fallback: the hot path needs it
-    raise ImportError(
-        "covalent_ssh_plugin_b200._b2host is not built: run `python -m covalent_ssh_plugin_b200.build` "
-        f"({_err})") from _err
+_b2host = None                     # compiled staging helper (hostext/b2host.c), loaded with the first engine
+
+
+def _load_b2host():
+    """Import the CPython staging helper.  Deferred to engine creation so that importing the package —
+    which `python -m covalent_ssh_plugin_b200.build` itself has to do — works in a tree that has not been
+    built yet.  Never a silent fallback: without the helper there is no engine."""
+    global _b2host
+    if _b2host is None:
+        try:
+            from . import _b2host as helper
+        except ImportError as err:
+            raise ImportError(
+                "covalent_ssh_plugin_b200._b2host is not built: run `python -m covalent_ssh_plugin_b200.build` "
+                f"({err})") from err
+        if helper.IDX_BITS != IDX_BITS or helper.TASK_BYTES != 64 or helper.JOB_BYTES != 24:
+            raise ImportError("covalent_ssh_plugin_b200._b2host does not match this source tree: rebuild it")
+        _b2host = helper
+    return _b2host
 
 _TASK = struct.Struct("<IIQQQQIIIIQ")
 assert _TASK.size == 64
@@ -52,7 +65,7 @@ _ELEMENTWISE = (L.K_COPY, L.K_SCALE_ADD, L.K_ADD, L.K_MUL, L.K_AXPY)
 _FAST1 = (L.K_COPY, L.K_SCALE_ADD, L.K_SUM)        # kinds the C stager takes in one call
 _FAST2 = (L.K_ADD, L.K_MUL, L.K_AXPY)
 _FASTI = (L.K_IADD, L.K_IMUL)
-IDX_BITS = _b2host.IDX_BITS
+IDX_BITS = 20                     # = B2H_IDX_BITS in hostext/b2host.c (checked when the helper loads)
 IDX_MASK = (1 << IDX_BITS) - 1
 MiB = 1 << 20
 
@@ -287,7 +300,7 @@ class DeviceEngine:
         self._jobs = [np.zeros(self._cap_jobs, dtype=L.JOB_DTYPE) for _ in range(self.n_segments)]
         self._jobs_addr = [j.ctypes.data for j in self._jobs]
         self._descs = [L.Batch() for _ in range(self.n_segments)]
-        self._stager = _b2host.Stager(np.ndarray)
+        self._stager = _load_b2host().Stager(np.ndarray)
         self._free_segments = list(range(self.n_segments - 1, -1, -1))
         self._free_out = list(range(self.n_out_segments - 1, -1, -1))
         self._seg_lock = threading.Lock()          # lease finalizers may run on any thread

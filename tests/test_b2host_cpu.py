@@ -4,10 +4,21 @@ leaves to the general Python path, what it writes.  CPU only — the helper neve
 import numpy as np
 import pytest
 
-from covalent_ssh_plugin_b200 import _b2host, _b2lib as L
+from covalent_ssh_plugin_b200 import _b2lib as L
+from covalent_ssh_plugin_b200.engine import IDX_BITS
 
-IDX_BITS = _b2host.IDX_BITS
 MASK = (1 << IDX_BITS) - 1
+_b2host = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def helper(built_library):
+    """The helper is imported only after the session fixture has built it (a fresh clone has no .so)."""
+    global _b2host
+    from covalent_ssh_plugin_b200.engine import _load_b2host
+
+    _b2host = _load_b2host()
+    return _b2host
 
 
 @pytest.fixture()
@@ -20,7 +31,7 @@ def stager():
 
 
 def test_record_sizes_match_the_header():
-    assert _b2host.TASK_BYTES == 64 and _b2host.JOB_BYTES == 24
+    assert _b2host.TASK_BYTES == 64 and _b2host.JOB_BYTES == 24 and _b2host.IDX_BITS == IDX_BITS
     assert np.dtype(L.TASK_DTYPE).itemsize == 64 and np.dtype(L.JOB_DTYPE).itemsize == 24
 
 
