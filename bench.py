@@ -26,7 +26,8 @@ i mod G.  A "step" is one pass of the whole lattice through ``SSHExecutor.run``.
   peer, bcast   (N > 1) K4 NVLink peer pack (bytes verified) and the shared-operand ncclBroadcast.
   cpu_baseline  the reference's CPU path on this box's host cores, bounded sample, median of 3
                 (``oracle/_ref`` = the unmodified reference when it was installed at build time,
-                else the oracle port), plus the in-process floor (cloudpickle round trips only).
+                else the oracle port), plus the in-process floor (cloudpickle round trips only) and
+                ``other_configs``: the reference beside C2 / C4 / C5 on bounded samples.
 """
 
 from __future__ import annotations
@@ -192,12 +193,89 @@ class Dist:
 
 
 # ------------------------------------------------------------- CPU baseline ---
-def _scale_add_calls(n_sample: int, payload: int):
-    from covalent_ssh_plugin_b200 import electrons
+# The electrons the REFERENCE runs are plain functions pickled BY VALUE, as a user's electrons are
+# ("function body pickled by value"): its remote interpreter imports numpy (ints:
+# nothing) and never this repository's package — importing it there would cost the reference ≈ 80 ms
+# of its ≈ 400 ms per interpreter.  Same arithmetic as covalent_ssh_plugin_b200/electrons.py.
+def _ref_scale_add(x):
+    return np.float32(2.0) * x + np.float32(1.0)
 
-    return [(electrons.scale_add,
+
+def _ref_add_int(a, b):
+    return a + b
+
+
+def _ref_plus_one(x):
+    return x + np.float32(1.0)
+
+
+def _ref_vec_mul(x, y):
+    return x * y
+
+
+def _ref_stack_sum(xs):
+    acc = xs[0].copy()
+    for x in xs[1:]:
+        acc += x
+    return acc
+
+
+def _by_value():
+    """cloudpickle pickles functions of ``__main__`` by value; make it so when bench.py is imported."""
+    if __name__ != "__main__":
+        import cloudpickle
+
+        try:
+            cloudpickle.register_pickle_by_value(sys.modules[__name__])
+        except Exception:
+            pass
+
+
+def _scale_add_calls(n_sample: int, payload: int):
+    return [(_ref_scale_add,
              [np.random.default_rng([0, i]).standard_normal(payload // 4, dtype=np.float32)], {})
             for i in range(n_sample)]
+
+
+def _reference_runner(tmp: str):
+    """(kind, run_pass(calls) coroutine function, cores): the unmodified reference from oracle/_ref
+    when it travelled (kind "reference"), else the restated port."""
+    from oracle import ref_harness, reference_port as P
+
+    _by_value()
+    cores = len(os.sched_getaffinity(0))
+    env_threads = {v: "1" for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    # One BLAS/OpenMP thread per remote interpreter: with `cores` interpreters in flight the default
+    # (a pool of `cores` threads EACH) oversubscribes the host and makes the reference ~10x slower
+    # (15 vs 150 electrons/s on the 128-core B200 host).  The baseline runs in its best configuration.
+    if ref_harness.available():
+        saved = {k: os.environ.get(k) for k in env_threads}
+        os.environ.update(env_threads)
+        try:
+            ex = ref_harness.make_executor(tmp, pythonpath=str(REPO))
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+        async def run_pass(batch):
+            out = []
+            for lo in range(0, len(batch), cores):
+                out += await asyncio.gather(*[
+                    ex.run(fn, list(a), dict(k), {"dispatch_id": "cpu", "node_id": lo + j})
+                    for j, (fn, a, k) in enumerate(batch[lo:lo + cores])])
+            return out
+
+        return "reference", run_pass, cores
+    s = P.PortSettings(tmp, pythonpath=str(REPO))
+    s.env.update(env_threads)
+
+    async def run_pass(batch):
+        return await P.run_many(s, batch, cores)
+
+    return "port", run_pass, cores
 
 
 def reference_cpu_sample(n_sample: int, payload: int, passes: int = 3, warmup: int = 0, budget_s: float = 120.0):
@@ -209,44 +287,12 @@ def reference_cpu_sample(n_sample: int, payload: int, passes: int = 3, warmup: i
     time into git-ignored ``oracle/_ref`` (oracle/make_ref.py), run under the stub ``covalent`` /
     local-transport ``asyncssh`` of oracle/ref_harness.py — no TCP, no crypto: strictly favourable to
     the reference.  kind "port": oracle/reference_port.py, when the reference did not travel."""
-    from oracle import ref_harness, reference_port as P
+    from oracle import ref_harness
 
-    cores = len(os.sched_getaffinity(0))
     calls = _scale_add_calls(n_sample, payload)
     times, done = [], []
     with tempfile.TemporaryDirectory(prefix="b2-cpu-") as tmp:
-        env_threads = {v: "1" for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
-        # One BLAS/OpenMP thread per remote interpreter: with `cores` interpreters in flight the default
-        # (a pool of `cores` threads EACH) oversubscribes the host and makes the reference ~10x slower
-        # (15 vs 150 electrons/s on the 128-core B200 host).  The baseline runs in its best configuration.
-        if ref_harness.available():
-            kind = "reference"
-            saved = {k: os.environ.get(k) for k in env_threads}
-            os.environ.update(env_threads)
-            try:
-                ex = ref_harness.make_executor(tmp, pythonpath=str(REPO))
-            finally:
-                for k, v in saved.items():
-                    if v is None:
-                        os.environ.pop(k, None)
-                    else:
-                        os.environ[k] = v
-
-            async def run_pass(batch):
-                out = []
-                for lo in range(0, len(batch), cores):
-                    out += await asyncio.gather(*[
-                        ex.run(fn, list(a), dict(k), {"dispatch_id": "cpu", "node_id": lo + j})
-                        for j, (fn, a, k) in enumerate(batch[lo:lo + cores])])
-                return out
-        else:
-            kind = "port"
-            s = P.PortSettings(tmp, pythonpath=str(REPO))
-            s.env.update(env_threads)
-
-            async def run_pass(batch):
-                return await P.run_many(s, batch, cores)
-
+        kind, run_pass, cores = _reference_runner(tmp)
         n_now = n_sample
         out = None
         for it in range(warmup + passes):
@@ -266,9 +312,73 @@ def reference_cpu_sample(n_sample: int, payload: int, passes: int = 3, warmup: i
               f"{len(times)} passes (median), through "
               + (f"the unmodified reference ssh.py+exec.py ({ref_harness.REFERENCE_ROOT}) under oracle/ref_harness.py"
                  if kind == "reference" else "oracle/reference_port.py")
-              + f" with the local transport, waves of {cores} coroutines, OMP/BLAS threads pinned to 1")
+              + f" with the local transport, waves of {cores} coroutines, OMP/BLAS threads pinned to 1, "
+                "the electron pickled by value (its remote interpreter imports numpy only)")
     return {"value": 1.0 / per_electron, "unit": "electrons/s", "cores": cores, "kind": kind, "sample": sample,
             "per_pass": per_pass, "seconds_per_electron": per_electron}
+
+
+def reference_other_configs(budget_s: float = 90.0):
+    """The reference beside C2, C4 and C5 (BASELINE.json configs[1,3,4]): bounded samples, one wave of
+    one coroutine per host core each, through the same runner as ``cpu_baseline``.  The reference has
+    no lattice driver (Covalent core resolves dependencies and calls ``run`` once per node with the
+    parents' results as arguments), so C4 is emulated exactly that way: root, a sample of the fan-out
+    in one wave, a reduce over the sample — and extrapolated to the 1 000 nodes, saying so."""
+    out = {}
+    t_start = time.perf_counter()
+    with tempfile.TemporaryDirectory(prefix="b2-cpu-") as tmp:
+        kind, run_pass, cores = _reference_runner(tmp)
+        wave = max(8, min(cores, 128))
+        out["kind"], out["cores"] = kind, cores
+
+        def timed_pass(calls):
+            t0 = time.perf_counter()
+            res = asyncio.run(run_pass(calls))
+            return time.perf_counter() - t0, res
+
+        # C2: int electrons (nothing but cloudpickle imported in the remote interpreter)
+        ints = [(i, 2 * i + 1) for i in range(wave)]
+        timed_pass([(_ref_add_int, [a, b], {}) for a, b in ints[:max(8, wave // 4)]])        # warm the page cache
+        dt, res = timed_pass([(_ref_add_int, [a, b], {}) for a, b in ints])
+        out["c2"] = {"value": len(ints) / dt, "unit": "electrons/s", "exact": res == [a + b for a, b in ints],
+                     "sample": f"{len(ints)} add_int electrons, one wave"}
+
+        # C5: one wave per payload size (fewer electrons for the largest: three files per electron)
+        rows = []
+        for size in (1 * KiB, 4 * KiB, 16 * KiB, 64 * KiB, 256 * KiB, 1 * MiB, 4 * MiB, 16 * MiB):
+            if time.perf_counter() - t_start > budget_s:
+                rows.append({"payload_bytes": size, "skipped": "time budget of the auxiliary block spent"})
+                continue
+            m = wave if size <= 1 * MiB else max(8, wave // 8)
+            calls = _scale_add_calls(m, size)
+            dt, res = timed_pass(calls)
+            ok = bool(np.array_equal(res[-1], np.float32(2.0) * calls[-1][1][0] + np.float32(1.0)))
+            rows.append({"payload_bytes": size, "electrons": m, "electrons_per_s": m / dt,
+                         "gbs_in_plus_out": 2.0 * m * size / dt / 1e9, "exact": ok})
+            del calls, res
+        out["c5"] = {"rows": rows, "sample": "one wave of scale_add electrons per payload size"}
+
+        # C4: root -> m x vec_mul(r, w_i) -> stack_sum over the m results, 1 MiB fp32 operands
+        nel, n_fan = 262144, 998
+        m = max(8, min(wave, 64))
+        rng = np.random.default_rng(4)
+        x0 = rng.random(nel, dtype=np.float32)
+        ws = [rng.random(nel, dtype=np.float32) for _ in range(m)]
+        t_root, r = timed_pass([(_ref_plus_one, [x0], {})])
+        t_fan, prods = timed_pass([(_ref_vec_mul, [r[0], w], {}) for w in ws])
+        t_red, total = timed_pass([(_ref_stack_sum, [prods], {})])
+        want = _ref_stack_sum([_ref_vec_mul(_ref_plus_one(x0), w) for w in ws])
+        waves = -(-n_fan // cores)
+        # the reduce = one electron's fixed cost (the root's) + what its m x 1 MiB of arguments added, scaled to 998
+        t_red_full = t_root + max(0.0, t_red - t_root) * (n_fan - 1) / max(1, m - 1)
+        out["c4"] = {"sampled_nodes": m + 2, "seconds_root": t_root, "seconds_fan_out_wave": t_fan,
+                     "seconds_reduce_of_sample": t_red, "exact": bool(np.array_equal(total[0], want)),
+                     "extrapolated_ms_1000_nodes": 1e3 * (t_root + waves * t_fan + t_red_full),
+                     "sample": f"root + {m} of the 998 fan-out electrons (one wave) + a reduce over those {m}; extrapolated as "
+                               f"root + ceil(998 / {cores} cores) fan-out waves + a reduce whose argument-dependent part "
+                               f"(reduce minus root) is scaled from {m} to 998 operands"}
+    out["seconds"] = time.perf_counter() - t_start
+    return out
 
 
 def t_floor_sample(n_sample: int, payload: int):
@@ -784,6 +894,11 @@ def run_cuda_arm(args, dist: Dist):
             cpu["t_floor"] = t_floor_sample(4096, payload)
         except Exception as err:     # never lose the line over the auxiliary number
             cpu["t_floor"] = {"error": repr(err)}
+        if not args.quick:
+            try:
+                cpu["other_configs"] = reference_other_configs()
+            except Exception as err:
+                cpu["other_configs"] = {"error": repr(err)[:300]}
 
     if rank == 0:
         line = {
