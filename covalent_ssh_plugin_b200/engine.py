@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import asyncio
 import ctypes as C
+import logging
 import os
 import queue
 import struct
@@ -35,6 +36,8 @@ import numpy as np
 
 from . import _b2lib as L
 from .electrons import DeviceElectron, DeviceRef, EncodedTask, decode, registry_size, registry_snapshot
+
+app_log = logging.getLogger(__name__)
 
 _b2host = None                     # compiled staging helper (hostext/b2host.c), loaded with the first engine
 
@@ -859,7 +862,10 @@ class DeviceEngine:
             try:
                 b.loop.call_soon_threadsafe(self._complete, b)
             except (RuntimeError, AttributeError):      # loop already closed / no loop
-                self._complete(b)
+                try:
+                    self._complete(b)
+                except Exception:                       # this thread serves every later batch: it stays up
+                    app_log.exception("completing a batch whose event loop is gone")
 
     def _complete(self, b: Batch) -> None:
         if b.done:
@@ -876,7 +882,10 @@ class DeviceEngine:
         waiters, b.waiters = b.waiters, []
         for fut in waiters:
             if not fut.done():
-                fut.set_result(None)
+                try:
+                    fut.set_result(None)
+                except RuntimeError:          # its loop was closed under it: nobody is left to wake
+                    pass
 
     def status_of(self, s: Staged) -> int:
         b = s.batch

@@ -443,3 +443,35 @@ def test_host_pool_honours_python_path_and_conda_env(fake_lib, tmp_path):
             assert asyncio.run(ex.run(electrons.add_int, [2, 3], {}, {"dispatch_id": "pp", "node_id": 7})) == 5
         finally:
             hostpool.shutdown()
+
+
+def test_a_loop_closed_under_pending_runs_does_not_take_the_engine_down(fake_lib, tmp_path):
+    """The completion thread serves every later batch: waking the waiters of a loop that was closed
+    with runs still pending must not end it."""
+    import threading
+    import time
+
+    engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path)
+    gate = threading.Event()
+    real_wait = fake_lib.b2_wait
+
+    def slow_wait(dev, ticket):
+        gate.wait(5)
+        return real_wait(dev, ticket)
+
+    fake_lib.b2_wait = slow_wait
+    x = np.arange(64, dtype=np.float32)
+    loop = asyncio.new_event_loop()
+    tasks = [loop.create_task(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "a", "node_id": i}))
+             for i in range(3)]
+    loop.run_until_complete(asyncio.sleep(0.05))       # staged and shipped; the completion thread sits in b2_wait
+    assert not any(t.done() for t in tasks)
+    loop.close()                                       # abnormal: pending runs abandoned with their loop
+    gate.set()
+    time.sleep(0.2)
+    fake_lib.b2_wait = real_wait
+    assert engine_mod.get_engine(0)._waiter.is_alive()
+    out = asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "b", "node_id": 0}))
+    assert np.array_equal(out, np.float32(2) * x + np.float32(1))
+    del tasks
