@@ -31,12 +31,22 @@ from . import _b2lib as L
 from .electrons import K_STACK_SUM, NotDeviceEligible, decode, lookup, plan_call
 from .engine import DeviceArray, DeviceEngine, get_engine
 
-__all__ = ["electron", "lattice", "dispatch", "get_result", "status", "Result"]
+__all__ = ["electron", "lattice", "dispatch", "get_result", "status", "Result", "DepsPip"]
 
 
 class status:                       # ct.status look-alike
     COMPLETED = "COMPLETED"
     FAILED = "FAILED"
+
+
+class DepsPip:
+    """``ct.DepsPip(packages=[...])`` as the reference's svm workflow builds it (svm_workflow.py:7,20).
+    Recorded on the electron, never applied: installing packages is Covalent core's job on a remote
+    host and there is no remote host here (the electron runs in this box's interpreter)."""
+
+    def __init__(self, packages=None, reqs_path: str = ""):
+        self.packages = list(packages or [])
+        self.reqs_path = reqs_path
 
 
 class Result:

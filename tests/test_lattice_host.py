@@ -217,3 +217,84 @@ def test_diamond_across_four_gpus(gpu):
     assert "demoted" not in r.stats and r.stats["device_electrons"] == 2 * 21 + 2
     for d in range(4):
         assert engine_mod.existing_engine(d).heap.bytes_in_use() == 0
+
+
+@pytest.fixture()
+def ssh_alias(gpu, tmp_path, monkeypatch):
+    """``executor="ssh"`` resolves through the user's covalent.conf, as Covalent's executor manager does."""
+    from covalent_ssh_plugin_b200 import _covalent_compat, hostpool
+
+    key = tmp_path / "k"
+    (tmp_path / "covalent.conf").write_text(
+        '[dispatcher]\ncache_dir = "%s"\n[executors.ssh]\nusername = "u"\nhostname = "cuda:0"\n'
+        'ssh_key_file = "%s"\nhost_pool = true\n' % (tmp_path, key))
+    monkeypatch.setenv("COVALENT_CONFIG_DIR", str(tmp_path))
+    monkeypatch.setattr(_covalent_compat, "_loaded", None)
+    yield
+    monkeypatch.setattr(_covalent_compat, "_loaded", None)
+    hostpool.shutdown()
+
+
+def test_reference_basic_workflow_with_the_ssh_alias(ssh_alias):
+    """basic_workflow_test.py:7-29, body unchanged: ``executor="ssh"`` on an electron that is plain Python
+    (not a registered device electron) runs in the host pool."""
+    @ct.electron(executor="ssh")
+    def join_words(a, b):
+        return ", ".join([a, b])
+
+    @ct.electron
+    def excitement(a):
+        return f"{a}!"
+
+    @ct.lattice
+    def basic_workflow(a, b):
+        phrase = join_words(a, b)
+        return excitement(phrase)
+
+    dispatch_id = ct.dispatch(basic_workflow)("Hello", "World")
+    result = ct.get_result(dispatch_id=dispatch_id, wait=True)
+    assert str(result.status) == str(ct.status.COMPLETED), result.error
+    assert result.result == "Hello, World!"
+
+
+def test_reference_svm_workflow_unchanged(ssh_alias):
+    """svm_workflow.py:1-46, body unchanged (DepsPip included): the SVC is trained by the ssh executor's
+    host pool and travels back as a pickled object."""
+    datasets = pytest.importorskip("sklearn.datasets")
+    svm = pytest.importorskip("sklearn.svm")
+    from numpy.random import permutation
+
+    deps_pip = ct.DepsPip(packages=["numpy==1.23.2", "scikit-learn==1.1.2"])
+
+    @ct.electron
+    def load_data():
+        iris = datasets.load_iris()
+        perm = permutation(iris.target.size)
+        iris.data = iris.data[perm]
+        iris.target = iris.target[perm]
+        return iris.data, iris.target
+
+    @ct.electron(executor="ssh", deps_pip=deps_pip)
+    def train_svm(data, C, gamma):
+        X, y = data
+        clf = svm.SVC(C=C, gamma=gamma)
+        clf.fit(X[90:], y[90:])
+        return clf
+
+    @ct.electron
+    def score_svm(data, clf):
+        X_test, y_test = data
+        return clf.score(X_test[:90], y_test[:90])
+
+    @ct.lattice
+    def run_experiment(C=1.0, gamma=0.7):
+        data = load_data()
+        clf = train_svm(data=data, C=C, gamma=gamma)
+        score = score_svm(data=data, clf=clf)
+        return score
+
+    dispatchable_func = ct.dispatch(run_experiment)
+    dispatch_id = dispatchable_func(C=1.0, gamma=0.7)
+    result = ct.get_result(dispatch_id=dispatch_id, wait=True)
+    assert str(result.status) == str(ct.status.COMPLETED), result.error
+    assert 0.5 < result.result <= 1.0
