@@ -31,12 +31,27 @@ from . import _b2lib as L
 from .electrons import K_STACK_SUM, NotDeviceEligible, decode, lookup, plan_call
 from .engine import DeviceArray, DeviceEngine, get_engine
 
-__all__ = ["electron", "lattice", "dispatch", "get_result", "status", "Result", "DepsPip"]
+__all__ = ["electron", "lattice", "dispatch", "get_result", "status", "Result", "DepsPip", "executor"]
 
 
 class status:                       # ct.status look-alike
     COMPLETED = "COMPLETED"
     FAILED = "FAILED"
+
+
+class _ExecutorNamespace:
+    """``ct.executor.SSHExecutor`` (README.md:55-60 of the reference); resolved on first use because
+    ``ssh.py`` imports this package."""
+
+    def __getattr__(self, name):
+        if name == "SSHExecutor":
+            from .ssh import SSHExecutor
+
+            return SSHExecutor
+        raise AttributeError(name)
+
+
+executor = _ExecutorNamespace()
 
 
 class DepsPip:

@@ -298,3 +298,30 @@ def test_reference_svm_workflow_unchanged(ssh_alias):
     result = ct.get_result(dispatch_id=dispatch_id, wait=True)
     assert str(result.status) == str(ct.status.COMPLETED), result.error
     assert 0.5 < result.result <= 1.0
+
+
+def test_readme_usage_with_an_executor_object(gpu, tmp_path):
+    """README.md:52-65 of the reference: ``ct.executor.SSHExecutor(...)`` handed to an electron."""
+    key = tmp_path / "k"
+    executor = ct.executor.SSHExecutor(username="user", hostname="cuda:1", ssh_key_file=str(key),
+                                       cache_dir=str(tmp_path))
+    assert isinstance(executor, SSHExecutor)
+
+    @ct.electron(executor=executor)
+    def my_custom_task(x, y):
+        return x + y
+
+    @ct.lattice
+    def wf(x, y):
+        return my_custom_task(x, y)
+
+    r = ct.get_result(ct.dispatch(wf)(3, 4))
+    # a plain-Python electron on a GPU "host" without the host pool: the reference's failure decision
+    assert r.status == ct.status.FAILED and isinstance(r.error, RuntimeError)
+
+    @ct.lattice
+    def wf2(x, y):
+        return ct.electron(E.add_int, executor=executor)(x, y)
+
+    r = ct.get_result(ct.dispatch(wf2)(3, 4))
+    assert r.status == ct.status.COMPLETED and r.result == 7 and type(r.result) is int
