@@ -23,6 +23,7 @@ has been read, so a batch is always one contiguous copy each way.
 from __future__ import annotations
 
 import asyncio
+import collections
 import ctypes as C
 import logging
 import os
@@ -38,6 +39,8 @@ from . import _b2lib as L
 from .electrons import DeviceElectron, DeviceRef, EncodedTask, decode, registry_size, registry_snapshot
 
 app_log = logging.getLogger(__name__)
+
+BACKPRESSURE = False               # stage_fast: eligible call, but no staging segment pair is free
 
 _b2host = None                     # compiled staging helper (hostext/b2host.c), loaded with the first engine
 
@@ -307,7 +310,7 @@ class DeviceEngine:
         self._free_segments = list(range(self.n_segments - 1, -1, -1))
         self._free_out = list(range(self.n_out_segments - 1, -1, -1))
         self._seg_lock = threading.Lock()          # lease finalizers may run on any thread
-        self._segment_waiters: list = []           # (loop, future)
+        self._segment_waiters: collections.deque = collections.deque()     # (loop, future) of parked stagers
         self._leases_out = 0                       # egress segments currently aliased by results
         self._open: Optional[Batch] = None
         self._inflight: List[Batch] = []
@@ -601,7 +604,8 @@ class DeviceEngine:
         operands are plain C-contiguous float32 ndarrays (or Python ints).  Writes the task record
         and the copy job(s) into the open batch and returns ``(batch, packed)`` with
         ``packed = out_off << IDX_BITS | index``; returns None when the general path
-        (``encode`` + ``stage``) has to look at this call."""
+        (``encode`` + ``stage``) has to look at this call, and ``BACKPRESSURE`` (False) when the
+        call is fine but no staging segment pair is free right now (``segment_wait`` and retry)."""
         kind = spec.kind
         nargs = len(args)
         st = self._stager
@@ -611,7 +615,7 @@ class DeviceEngine:
                 self.flush()
             b = self._open_batch(loop)
             if b is None:
-                return None
+                return BACKPRESSURE
         if spec.fn_id > self._registered:
             self.sync_registry()
         for _ in range(2):
@@ -634,8 +638,14 @@ class DeviceEngine:
             self.flush()                       # the open batch is full: ship it, retry in a new one
             b = self._open_batch(loop)
             if b is None:
-                return None
+                return BACKPRESSURE
         return None
+
+    def segment_wait(self, loop):
+        """A future of ``loop`` that completes when a staging segment pair may be free again."""
+        fut = loop.create_future()
+        self._segment_waiters.append((loop, fut))
+        return fut
 
     def waiter(self, b: Batch, loop):
         """A future of ``loop`` that completes when batch ``b`` has (one per electron: cancelling
@@ -665,9 +675,7 @@ class DeviceEngine:
             if b is None:
                 b = self._open_batch(loop)
                 if b is None:
-                    fut = loop.create_future()
-                    self._segment_waiters.append((loop, fut))
-                    await fut
+                    await self.segment_wait(loop)
                     continue
             break
         return self._append(b, enc)
@@ -996,14 +1004,33 @@ class DeviceEngine:
         self._wake_waiters()
 
     def _wake_waiters(self) -> None:
-        """A segment came back: wake EVERY stager parked on the pool.  The first one opens a
-        batch, the others join it — waking one at a time shipped one-electron batches."""
-        while self._segment_waiters:
+        """Segments came back: wake the stagers parked on the pool — one batch worth per free
+        segment pair.  (Waking one at a time shipped one-electron batches: the first opens a batch,
+        the others must be there to join it.  Waking all of them on every release costs a wake-up
+        and a re-park per parked electron per batch.)  Nothing is woken while no PAIR is free: a
+        stager needs an ingress and an egress segment."""
+        waiters = self._segment_waiters
+        if not waiters:
+            return
+        with self._seg_lock:
+            pairs = min(len(self._free_segments), len(self._free_out))
+        if pairs == 0:
+            return
+        try:
+            here = asyncio.get_running_loop()
+        except RuntimeError:
+            here = None
+        budget = pairs * self.max_batch
+        while budget > 0:
             try:
-                loop, fut = self._segment_waiters.pop(0)
+                loop, fut = waiters.popleft()
             except IndexError:
                 return
             if fut.done():
+                continue
+            budget -= 1
+            if loop is here:
+                fut.set_result(None)
                 continue
             try:
                 loop.call_soon_threadsafe(_resolve, fut)

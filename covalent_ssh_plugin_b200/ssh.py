@@ -37,7 +37,7 @@ from typing import Any, Callable, Coroutine, Dict, Optional, Tuple, Union
 
 from . import _b2lib, hostpool
 from .electrons import ATTR as _ELECTRON_ATTR, NotDeviceEligible, encode
-from .engine import IDX_BITS, IDX_MASK, DeviceEngine, Staged, get_engine
+from .engine import BACKPRESSURE, IDX_BITS, IDX_MASK, DeviceEngine, Staged, get_engine
 
 try:  # the real Covalent SDK, when installed
     from covalent._shared_files import logger as _cov_logger
@@ -523,6 +523,9 @@ class SSHExecutor(RemoteExecutor):
                 engine = conn.engine
                 loop = asyncio.get_running_loop()
                 got = engine.stage_fast(loop, spec, args)
+                while got is BACKPRESSURE:                  # every staging segment is in flight: park, retry
+                    await engine.segment_wait(loop)
+                    got = engine.stage_fast(loop, spec, args)
                 if got is not None:
                     batch, packed = got
                     index = packed & IDX_MASK

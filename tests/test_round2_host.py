@@ -475,3 +475,50 @@ def test_a_loop_closed_under_pending_runs_does_not_take_the_engine_down(fake_lib
     out = asyncio.run(ex.run(electrons.scale_add, [x], {}, {"dispatch_id": "b", "node_id": 0}))
     assert np.array_equal(out, np.float32(2) * x + np.float32(1))
     del tasks
+
+
+def test_back_pressure_keeps_the_fused_path(fake_lib, tmp_path, monkeypatch):
+    """With every staging segment in flight a fused run() parks and retries the one-call staging; it
+    does not drop to the step-by-step body (eight awaited helpers per electron), and a release wakes
+    a batch worth of parked electrons, not one and not all."""
+    fake_lib.delay_polls = 3
+    eng = engine_mod.get_engine(0, **SMALL)                    # 4 x 4 MiB segments, 16 electrons per batch
+    ex = make_executor(tmp_path)
+    general = []
+    real_stage = eng.stage
+
+    async def counted_stage(enc):
+        general.append(enc)
+        return await real_stage(enc)
+
+    monkeypatch.setattr(eng, "stage", counted_stage)
+    parked_peak = [0]
+    real_wait = eng.segment_wait
+
+    def counted_wait(loop):
+        fut = real_wait(loop)
+        parked_peak[0] = max(parked_peak[0], len(eng._segment_waiters))
+        return fut
+
+    monkeypatch.setattr(eng, "segment_wait", counted_wait)
+    n = 400
+    xs = [np.random.default_rng(i).standard_normal(16384, dtype=np.float32) for i in range(n)]
+
+    async def go():
+        return await asyncio.gather(*[
+            ex.run(electrons.scale_add, [xs[i]], {}, {"dispatch_id": "bp2", "node_id": i}) for i in range(n)])
+
+    asyncio.run(ex.run(electrons.add_int, [1, 2], {}, {"dispatch_id": "bp2", "node_id": "open"}))   # opens the connection
+    general.clear()
+    base = eng.counters["batches"]
+    out = asyncio.run(go())
+    for i in range(n):
+        assert np.array_equal(out[i], np.float32(2.0) * xs[i] + np.float32(1.0))
+    assert not general, "electrons left the fused path under back-pressure"
+    assert parked_peak[0] >= n - 4 * 16                        # it really was back-pressured
+    assert eng.counters["batches"] - base <= 2 * (n // 16)     # batches stay (nearly) full
+    del out
+    import gc
+
+    gc.collect()
+    assert sorted(eng._free_segments) == [0, 1, 2, 3] and not eng._segment_waiters

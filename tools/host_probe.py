@@ -75,6 +75,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--ints", action="store_true")
+    ap.add_argument("--tight", action="store_true",
+                    help="back-pressure shape: 1 GiB staging in 32 segments, 256-electron batches — the results "
+                         "of one step need more egress segments than there are")
     args = ap.parse_args()
 
     L._lib = NullLib(n_devices=1)
@@ -85,8 +88,11 @@ def main():
     count = payload // 4
     per_seg = 4096 * (payload + 256) + (1 << 20)
     nb = -(-n // 4096)
-    eng = get_engine(0, arena_bytes=(nb + 1 + 2 * nb + 4) * per_seg + (64 << 20), staging_bytes=(nb + 1) * per_seg,
-                     n_segments=nb + 1, n_out_segments=2 * nb + 4, max_batch=4096, queue_cap=1 << 16)
+    if args.tight:
+        eng = get_engine(0, arena_bytes=3 << 30, staging_bytes=1 << 30, n_segments=32, max_batch=256)
+    else:
+        eng = get_engine(0, arena_bytes=(nb + 1 + 2 * nb + 4) * per_seg + (64 << 20), staging_bytes=(nb + 1) * per_seg,
+                         n_segments=nb + 1, n_out_segments=2 * nb + 4, max_batch=4096, queue_cap=1 << 16)
     tmp = tempfile.mkdtemp(prefix="b2-probe-")
     key = Path(tmp) / "id_stub"
     key.touch()
@@ -121,7 +127,8 @@ def main():
         best = min(best, dt)
         del out
     print(f"{n} electrons x {payload} B: best {1e3 * best:.1f} ms/step = {1e6 * best / n:.2f} us/electron "
-          f"= {n / best / 1e3:.1f} k electrons/s (host only, null device)")
+          f"= {n / best / 1e3:.1f} k electrons/s (host only, null device); batches {eng.counters['batches']}, "
+          f"zero-copy batches {eng.counters['zero_copy_batches']}")
     shutdown_all()
 
 
