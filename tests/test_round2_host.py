@@ -481,7 +481,16 @@ def test_back_pressure_keeps_the_fused_path(fake_lib, tmp_path, monkeypatch):
     """With every staging segment in flight a fused run() parks and retries the one-call staging; it
     does not drop to the step-by-step body (eight awaited helpers per electron), and a release wakes
     a batch worth of parked electrons, not one and not all."""
-    fake_lib.delay_polls = 3
+    import time
+
+    fake_lib.delay_polls = 10 ** 9                             # batches finish through b2_wait only ...
+    real_wait = fake_lib.b2_wait
+
+    def slow_wait(dev, ticket):                                # ... and each takes a while
+        time.sleep(0.004)
+        return real_wait(dev, ticket)
+
+    fake_lib.b2_wait = slow_wait
     eng = engine_mod.get_engine(0, **SMALL)                    # 4 x 4 MiB segments, 16 electrons per batch
     ex = make_executor(tmp_path)
     general = []
@@ -493,10 +502,10 @@ def test_back_pressure_keeps_the_fused_path(fake_lib, tmp_path, monkeypatch):
 
     monkeypatch.setattr(eng, "stage", counted_stage)
     parked_peak = [0]
-    real_wait = eng.segment_wait
+    real_park = eng.segment_wait
 
     def counted_wait(loop):
-        fut = real_wait(loop)
+        fut = real_park(loop)
         parked_peak[0] = max(parked_peak[0], len(eng._segment_waiters))
         return fut
 
