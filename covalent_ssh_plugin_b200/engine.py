@@ -641,6 +641,11 @@ class DeviceEngine:
                 return BACKPRESSURE
         return None
 
+    def pass_wakeup(self) -> None:
+        """A parked stager is leaving without staging (cancelled): if it had been woken for a free
+        segment pair, somebody else has to be."""
+        self._wake_waiters()
+
     def segment_wait(self, loop):
         """A future of ``loop`` that completes when a staging segment pair may be free again."""
         fut = loop.create_future()
@@ -675,7 +680,11 @@ class DeviceEngine:
             if b is None:
                 b = self._open_batch(loop)
                 if b is None:
-                    await self.segment_wait(loop)
+                    try:
+                        await self.segment_wait(loop)
+                    except BaseException:
+                        self.pass_wakeup()
+                        raise
                     continue
             break
         return self._append(b, enc)

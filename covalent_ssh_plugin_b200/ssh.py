@@ -524,7 +524,11 @@ class SSHExecutor(RemoteExecutor):
                 loop = asyncio.get_running_loop()
                 got = engine.stage_fast(loop, spec, args)
                 while got is BACKPRESSURE:                  # every staging segment is in flight: park, retry
-                    await engine.segment_wait(loop)
+                    try:
+                        await engine.segment_wait(loop)
+                    except BaseException:                   # cancelled while parked, perhaps after being woken:
+                        engine.pass_wakeup()                # the wake-up must not die with this electron
+                        raise
                     got = engine.stage_fast(loop, spec, args)
                 if got is not None:
                     batch, packed = got

@@ -531,3 +531,98 @@ def test_back_pressure_keeps_the_fused_path(fake_lib, tmp_path, monkeypatch):
 
     gc.collect()
     assert sorted(eng._free_segments) == [0, 1, 2, 3] and not eng._segment_waiters
+
+
+def test_cancelling_parked_electrons_never_strands_the_others(fake_lib, tmp_path):
+    """Electrons parked for a staging segment that are cancelled — also just after having been woken — hand
+    the wake-up on: everybody else still runs, and nothing stays claimed."""
+    import time
+
+    fake_lib.delay_polls = 10 ** 9
+    real_wait = fake_lib.b2_wait
+
+    def slow_wait(dev, ticket):
+        time.sleep(0.003)
+        return real_wait(dev, ticket)
+
+    fake_lib.b2_wait = slow_wait
+    eng = engine_mod.get_engine(0, **SMALL)
+    ex = make_executor(tmp_path)
+    asyncio.run(ex.run(electrons.add_int, [1, 2], {}, {"dispatch_id": "cp", "node_id": "open"}))
+    n = 300
+    xs = [np.random.default_rng(i).standard_normal(16384, dtype=np.float32) for i in range(n)]
+    doomed = set(range(70, 300, 3))                           # all of them beyond the first 64: parked
+
+    async def go():
+        loop = asyncio.get_running_loop()
+        tasks = [loop.create_task(ex.run(electrons.scale_add, [xs[i]], {}, {"dispatch_id": "cp", "node_id": i}))
+                 for i in range(n)]
+        await asyncio.sleep(0)                                # everybody staged or parked
+        assert len(eng._segment_waiters) >= n - 64
+        for i in sorted(doomed)[::2]:
+            tasks[i].cancel()                                 # cancelled while parked
+        # the rest of the doomed ones are cancelled the moment a release has woken them
+        real_wake = eng._wake_waiters
+
+        def wake_then_cancel():
+            real_wake()
+            for i in sorted(doomed)[1::2]:
+                if not tasks[i].done():
+                    tasks[i].cancel()
+
+        eng._wake_waiters = wake_then_cancel
+        try:
+            return await asyncio.wait_for(asyncio.gather(*tasks, return_exceptions=True), timeout=60)
+        finally:
+            del eng._wake_waiters
+
+    out = asyncio.run(go())
+    for i in range(n):
+        if i in doomed:
+            assert isinstance(out[i], asyncio.CancelledError)
+        else:
+            assert np.array_equal(out[i], np.float32(2.0) * xs[i] + np.float32(1.0)), i
+    del out
+    import gc
+
+    gc.collect()
+    assert sorted(eng._free_segments) == [0, 1, 2, 3] and sorted(eng._free_out) == [0, 1, 2, 3]
+    assert not any(not f.done() for _, f in eng._segment_waiters) and not impl._live
+
+
+def test_a_woken_then_cancelled_electron_hands_its_wakeup_on(fake_lib, tmp_path):
+    """One pair comes back, one parked electron is woken for it and cancelled before it runs: the next
+    parked electron must get the pair (nothing else will ever wake it)."""
+    eng = engine_mod.get_engine(0, **{**SMALL, "max_batch": 1})         # one electron per batch: one wake-up per pair
+    ex = make_executor(tmp_path)
+    asyncio.run(ex.run(electrons.add_int, [1, 2], {}, {"dispatch_id": "hw", "node_id": "open"}))
+    with eng._seg_lock:
+        ins, outs = list(eng._free_segments), list(eng._free_out)
+        eng._free_segments.clear()
+        eng._free_out.clear()
+    xs = [np.full(256, i, dtype=np.float32) for i in range(3)]
+
+    async def go():
+        loop = asyncio.get_running_loop()
+        tasks = [loop.create_task(ex.run(electrons.scale_add, [xs[i]], {}, {"dispatch_id": "hw", "node_id": i}))
+                 for i in range(3)]
+        await asyncio.sleep(0)
+        assert len(eng._segment_waiters) == 3
+        with eng._seg_lock:
+            eng._free_segments.append(ins.pop())
+            eng._free_out.append(outs.pop())
+        eng._wake_waiters()                                   # wakes exactly one (budget = 1 pair x max_batch 1)
+        assert sum(f.done() for _, f in eng._segment_waiters) == 0 and len(eng._segment_waiters) == 2
+        tasks[0].cancel()                                     # ... which is cancelled before it gets to run
+        done = await asyncio.wait_for(asyncio.gather(*tasks, return_exceptions=True), timeout=20)
+        return done
+
+    try:
+        out = asyncio.run(go())
+    finally:
+        with eng._seg_lock:
+            eng._free_segments.extend(ins)
+            eng._free_out.extend(outs)
+    assert isinstance(out[0], asyncio.CancelledError)
+    assert np.array_equal(out[1], np.float32(2.0) * xs[1] + np.float32(1.0))
+    assert np.array_equal(out[2], np.float32(2.0) * xs[2] + np.float32(1.0))
