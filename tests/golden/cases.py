@@ -16,6 +16,32 @@ def f32(seed, shape, order="C", dist="normal", view=None):
     return ("f32", seed, tuple(shape) if not isinstance(shape, int) else (shape,), order, dist, view)
 
 
+# IEEE-754 corner values as bit patterns: signed zeros, the smallest / largest subnormals, the smallest
+# normal, values whose 2x+1 or x/2 is a rounding tie, the largest finite, infinities (and, for pure copies,
+# NaNs with payloads).  A device that flushes subnormals, fuses 2x+1 into one rounding or canonicalises
+# copied NaNs produces different bytes than the reference's numpy on the CPU.
+_SPECIAL_BITS = [0x00000000, 0x80000000, 0x00000001, 0x80000001, 0x00000003, 0x007FFFFF, 0x807FFFFF, 0x00800000,
+                 0x80800000, 0x00800001, 0x3F800000, 0xBF800000, 0x3F800001, 0x3F7FFFFF, 0x4B000001, 0x4B7FFFFF,
+                 0xCB000001, 0x4B800001, 0x33800000, 0x33800001, 0x337FFFFF, 0xB3800000, 0x7F7FFFFF, 0xFF7FFFFF,
+                 0x7F000000, 0x7EFFFFFF, 0x7F800000, 0xFF800000, 0x3EAAAAAB, 0x40490FDB, 0x00000002, 0x80000002]
+_NAN_BITS = [0x7FC00000, 0xFFC00000, 0x7FC12345, 0x7F800001, 0xFFABCDEF]
+
+
+def _specials(rng, n, with_nan=False):
+    bits = list(_SPECIAL_BITS) + (list(_NAN_BITS) if with_nan else [])
+    out = np.empty(n, dtype=np.uint32)
+    table = np.array(bits, dtype=np.uint32)
+    out[:] = table[np.arange(n) % len(table)]
+    # every third element: a random subnormal or a value a few ulps from a power of two
+    k = np.arange(n) % 3 == 2
+    rnd = rng.integers(0, 1 << 23, size=n, dtype=np.uint32)
+    sign = rng.integers(0, 2, size=n, dtype=np.uint32) << np.uint32(31)
+    sub = sign | rnd                                                  # exponent 0: subnormals
+    near = (np.uint32(0x3F800000) + (rnd & np.uint32(7)) - np.uint32(3)) | sign
+    out[k] = np.where(rnd[k] & np.uint32(8), sub[k], near[k])
+    return out.view(np.float32)
+
+
 def build_arg(recipe):
     """Materialise one argument from its recipe."""
     if recipe[0] == "int":
@@ -25,7 +51,10 @@ def build_arg(recipe):
         rng = np.random.default_rng([0, seed])
         full = tuple(2 * s for s in shape) if view == "stride2" else shape
         n = int(np.prod(full, dtype=np.int64))
-        flat = rng.standard_normal(n, dtype=np.float32) if dist == "normal" else rng.random(n, dtype=np.float32)
+        if dist in ("specials", "specials_nan"):
+            flat = _specials(rng, n, with_nan=dist == "specials_nan")
+        else:
+            flat = rng.standard_normal(n, dtype=np.float32) if dist == "normal" else rng.random(n, dtype=np.float32)
         arr = flat.reshape(full, order="C")
         if order == "F":
             arr = np.asfortranarray(arr)
@@ -103,6 +132,13 @@ CASES = [
     ("stack_sum_3x5", "stack_sum", [("f32list", 31, 3, (5,))]),
     ("stack_sum_17x1000", "stack_sum", [("f32list", 32, 17, (1000,))]),
     ("stack_sum_64x4096", "stack_sum", [("f32list", 33, 64, (4096,))]),
+    # ---- IEEE-754 corner values (subnormals, signed zeros, ties, overflow to inf; NaNs for copies) ----
+    ("identity_specials_nan", "identity", [f32(40, 4099, dist="specials_nan")]),
+    ("scale_add_specials", "scale_add", [f32(41, 4099, dist="specials")]),
+    ("plus_one_specials", "plus_one", [f32(42, 1031, dist="specials")]),
+    ("vec_add_specials", "vec_add", [f32(43, 4099, dist="specials"), f32(44, 4099)]),
+    ("vec_mul_specials", "vec_mul", [f32(45, 4099, dist="specials"), f32(46, 4099)]),
+    ("axpy_half_specials", "axpy_half", [f32(47, 4099, dist="specials"), f32(48, 4099, dist="specials")]),
     # ---- behaviours that never reach the device ---------------------------------
     ("raises_value_error", "raise_value_error", [("lit", "boom"), ("lit", 7)]),
     ("plain_python_join", "plain_python", [("lit", "Hello"), ("lit", "World")]),
